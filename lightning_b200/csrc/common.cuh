@@ -1,0 +1,41 @@
+// common.cuh — shared macros for the sm_100a secp256k1 verification engine.
+//
+// All arithmetic above the 256-bit primitives in u256.cuh is written as portable C++ marked
+// SV_HD.  On the device the primitives are inline-PTX carry chains that ptxas fuses into
+// IMAD.WIDE.U32(.X); when the same headers are compiled by g++ (tests/host_emul only — a
+// developer aid that lets the kernel source be unit-tested without a GPU, never linked into
+// the product library) they fall back to uint64_t arithmetic.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+// under nvcc everything is device-only: the product has NO host implementation of the maths
+#define SV_HD __device__ __forceinline__
+#define SV_D __device__ __forceinline__
+#define SV_HD_NOINLINE __device__ __noinline__
+#else
+#define SV_HD static inline
+#define SV_D static inline
+#define SV_HD_NOINLINE static
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define SV_DEVICE_CODE 1
+#define SV_UNROLL _Pragma("unroll")
+#else
+#define SV_DEVICE_CODE 0
+#define SV_UNROLL
+#endif
+
+// Constant tables live in __constant__ memory on the device; accesses with compile-time indices
+// (the arithmetic is fully unrolled) become immediates / uniform-register loads.
+#if defined(__CUDACC__)
+#define SV_CDATA __device__ __constant__
+#else
+#define SV_CDATA
+#endif
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;

@@ -1,0 +1,420 @@
+// verify.cuh — one signature verification, split the way the engine's kernels run it:
+//
+//   scalar side  (K_prep) : parse/range-check (r,s), s^-1 (amortised over a small batch with
+//                           Montgomery's trick), u1 = m/s, u2 = r/s, GLV split of u2, window
+//                           recoding  ->  128-byte sv_work record
+//   curve side   (K_main) : key decode (33-byte compressed / 64-byte x|y / 32-byte x-only),
+//                           per-key odd-multiples table, fixed-window ladder for u2*Q, fixed-base
+//                           comb for u1*G, final x (and y-parity) comparison  ->  verdict
+//
+// Accept/reject rules are those of the reference, bit for bit:
+//   ECDSA  : secp256k1_ecdsa_signature_parse_compact (secp256k1.c:377-396) + secp256k1_ecdsa_verify
+//            (secp256k1.c:442-456) + secp256k1_ecdsa_sig_verify (ecdsa_impl.h:195-264)
+//            + secp256k1_eckey_pubkey_parse (eckey_impl.h:17-35)
+//   Schnorr: secp256k1_xonly_pubkey_parse (modules/extrakeys/main_impl.h:23-43)
+//            + secp256k1_schnorrsig_verify (modules/schnorrsig/main_impl.h:219-265)
+// The double-scalar multiplication is NOT the reference's Strauss-wNAF (ecmult_impl.h:234-341):
+// wNAF digit positions are data dependent, which would make the 32 lanes of a warp add at
+// different ladder steps.  Here every lane executes the same schedule:
+//   u2*Q : GLV split (same endomorphism as scalar_impl.h:138-176), both halves forced odd, regular
+//          signed-odd-digit recoding with 4-bit windows -> 33 windows, 128 doublings, 65 mixed adds
+//          against an 8-entry odd-multiples table kept effective-affine by the isomorphism trick of
+//          ecmult_impl.h:73-115;
+//   u1*G : signed 16-bit comb over a precomputed affine table of d*2^(16 i)*G (gtable.cuh): 16 mixed
+//          adds, no doublings.  (Reference: 2 x 8192-entry wNAF tables, precomputed_ecmult.c.)
+#pragma once
+#include "ge.cuh"
+#include "sc.cuh"
+#include "sha256.cuh"
+
+#define SV_KIND_ECDSA33 0   // msg32 | pub33 (02/03 || x) | sig64 (r||s)
+#define SV_KIND_ECDSA_XY 1  // msg32 | pubxy64 (x || y)   | sig64 (r||s)      (pre-decompressed key)
+#define SV_KIND_SCHNORR 2   // msg32 | xonly32            | sig64 (R.x||s)    BIP-340
+
+// G comb table geometry: rows 0..14 hold d*B_i for d = 1..32768, row 15 holds d = 1..65536
+#define SV_GT_ROW 32768
+#define SV_GT_ENTRIES (15 * SV_GT_ROW + 65536)
+
+struct alignas(16) ge_mem {  // affine point as stored in HBM: 64 bytes, 4 x LDG.128
+    u32 x[8], y[8];
+};
+struct alignas(16) qtab_entry {  // per-verification odd-multiples scratch entry (96 bytes)
+    u32 x[8], y[8], h[8];
+};
+
+SV_HD void ge_from_mem(ge& r, const ge_mem* p) {
+#if SV_DEVICE_CODE
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+    r.x.v[0] = a.x; r.x.v[1] = a.y; r.x.v[2] = a.z; r.x.v[3] = a.w;
+    r.x.v[4] = b.x; r.x.v[5] = b.y; r.x.v[6] = b.z; r.x.v[7] = b.w;
+    r.y.v[0] = c.x; r.y.v[1] = c.y; r.y.v[2] = c.z; r.y.v[3] = c.w;
+    r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
+#else
+    for (int i = 0; i < 8; i++) { r.x.v[i] = p->x[i]; r.y.v[i] = p->y[i]; }
+#endif
+}
+SV_HD void ge_to_mem(ge_mem* p, const ge& a) {
+#if SV_DEVICE_CODE
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(a.x.v[0], a.x.v[1], a.x.v[2], a.x.v[3]);
+    q[1] = make_uint4(a.x.v[4], a.x.v[5], a.x.v[6], a.x.v[7]);
+    q[2] = make_uint4(a.y.v[0], a.y.v[1], a.y.v[2], a.y.v[3]);
+    q[3] = make_uint4(a.y.v[4], a.y.v[5], a.y.v[6], a.y.v[7]);
+#else
+    for (int i = 0; i < 8; i++) { p->x[i] = a.x.v[i]; p->y[i] = a.y.v[i]; }
+#endif
+}
+SV_HD void fe_from_words(fe& r, const u32* p) {
+#if SV_DEVICE_CODE
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) r.v[i] = p[i];
+#endif
+}
+SV_HD void fe_to_words(u32* p, const fe& a) {
+#if SV_DEVICE_CODE
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+#else
+    for (int i = 0; i < 8; i++) p[i] = a.v[i];
+#endif
+}
+
+// =================================================================================================
+// scalar side
+// =================================================================================================
+
+// ECDSA: parse (r,s) and the message hash.  Returns false (verdict 0) for r >= n, s >= n
+// (parse_compact, secp256k1.c:388-392), r == 0, s == 0 (ecdsa_impl.h:204), s > n/2
+// (secp256k1.c:451).  The message is reduced mod n and never rejected (secp256k1.c:449).
+SV_HD bool ecdsa_parse(sc& r, sc& s, sc& m, const u8* sig64, const u8* msg32) {
+    bool ovr, ovs;
+    sc_set_b32(r, sig64, &ovr);
+    sc_set_b32(s, sig64 + 32, &ovs);
+    sc_set_b32(m, msg32, nullptr);
+    bool ok = !ovr && !ovs && !sc_is_zero(r) && !sc_is_zero(s) && !sc_is_high(s);
+    return ok;
+}
+
+SV_HD void work_set_invalid(sv_work& w) {
+    SV_UNROLL
+    for (int i = 0; i < 5; i++) { w.k1[i] = 0; w.k2[i] = 0; w.pad[i] = 0; }
+    w.k1[0] = 1;
+    w.k2[0] = 1;
+    SV_UNROLL
+    for (int i = 0; i < 16; i++) w.gd[i] = 0;
+    w.flags = 0;
+}
+
+// ECDSA: given s^-1, finish the record: u1 = m/s, u2 = r/s (ecdsa_impl.h:209-211)
+SV_HD void ecdsa_finish_prep(sv_work& w, bool ok, const sc& r, const sc& m, const sc& sinv) {
+    if (!ok) {
+        work_set_invalid(w);
+        return;
+    }
+    sc u1, u2;
+    sc_mul(u1, sinv, m);
+    sc_mul(u2, sinv, r);
+    sc_prepare_u2(w, u2);
+    sc_prepare_u1(w, u1);
+    // second x candidate r + n exists iff r < p - n (ecdsa_impl.h:253-259; constant :32-34)
+    const u32 pmn[8] = {0x2FC9BAEEu, 0x402DA172u, 0x50B75FC4u, 0x45512319u, 0x00000001u, 0, 0, 0};
+    u32 t[8];
+    u32 bw = u256_sub(t, r.v, pmn);
+    w.flags = SV_WF_VALID | (bw ? SV_WF_R_PLUS_N : 0u);
+    SV_UNROLL
+    for (int i = 0; i < 5; i++) w.pad[i] = 0;
+}
+
+// BIP-340: R = s*G + (-e)*P with e = H_tag(r || P.x || m) mod n.   Rejects r >= p
+// (main_impl.h:235) and s >= n (:239-242).
+SV_HD void schnorr_prep(sv_work& w, const u8* sig64, const u8* xonly32, const u8* msg32) {
+    fe rx;
+    bool ovs;
+    sc s, e, ne;
+    bool ok = fe_set_b32(rx, sig64);
+    sc_set_b32(s, sig64 + 32, &ovs);
+    ok = ok && !ovs;
+    if (!ok) {
+        work_set_invalid(w);
+        return;
+    }
+    u8 h[32];
+    sha256_bip340_challenge(h, sig64, xonly32, msg32);
+    sc_set_b32(e, h, nullptr);
+    sc_negate(ne, e);
+    sc_prepare_u2(w, ne);
+    sc_prepare_u1(w, s);
+    w.flags = SV_WF_VALID;
+    SV_UNROLL
+    for (int i = 0; i < 5; i++) w.pad[i] = 0;
+}
+
+// Montgomery's trick: invert n (<= SV_PREP_BATCH) non-zero scalars with ONE exponentiation.
+#define SV_PREP_BATCH 16
+SV_HD void sc_batch_inverse(sc* v, int n) {
+    sc pre[SV_PREP_BATCH];
+    sc acc;
+    pre[0] = v[0];
+    for (int i = 1; i < n; i++) sc_mul(pre[i], pre[i - 1], v[i]);
+    sc_inverse(acc, pre[n - 1]);
+    for (int i = n - 1; i > 0; i--) {
+        sc t;
+        sc_mul(t, acc, pre[i - 1]);  // = 1 / v[i]
+        sc_mul(acc, acc, v[i]);
+        v[i] = t;
+    }
+    v[0] = acc;
+}
+
+// =================================================================================================
+// curve side
+// =================================================================================================
+
+// decode the public key of item `kind`; false -> verdict 0
+SV_HD bool key_decode(ge& Q, int kind, const u8* key) {
+    if (kind == SV_KIND_ECDSA33) {
+        // eckey_impl.h:17-20: prefix must be 02/03, x < p, x^3+7 a residue
+        u8 pfx = key[0];
+        fe x;
+        bool ok = (pfx == 2 || pfx == 3);
+        ok = fe_set_b32(x, key + 1) && ok;
+        if (!ok) return false;
+        return ge_set_xo(Q, x, pfx == 3);
+    } else if (kind == SV_KIND_ECDSA_XY) {
+        // eckey_impl.h:21-33 (65-byte form without the 04 prefix): x,y < p and on the curve
+        bool ok = fe_set_b32(Q.x, key);
+        ok = fe_set_b32(Q.y, key + 32) && ok;
+        if (!ok) return false;
+        return ge_is_on_curve(Q);
+    } else {
+        // extrakeys/main_impl.h:32-38: x < p, lift to the even-y point
+        fe x;
+        if (!fe_set_b32(x, key)) return false;
+        return ge_set_xo(Q, x, false);
+    }
+}
+
+SV_HD u32 window4(const u32 mag[5], int i) {  // bits [4i+1, 4i+5) of the 160-bit magnitude
+    int off = 4 * i + 1;
+    int l = off >> 5, sh = off & 31;
+    u64 two = ((u64)(l < 4 ? mag[l + 1] : 0u) << 32) | mag[l];
+    return (u32)(two >> sh) & 15u;
+}
+
+// Build the effective-affine table of {1,3,...,15}*Q in `tab` (x,y valid on return) and return
+// the common Z of the table in true curve coordinates (zc).  124 field mul/sqr.
+SV_HD void qtable_build(qtab_entry* tab, fe& zc, const ge& Q) {
+    gej D, acc;
+    gej_set_ge(D, Q);
+    gej_double(D, D);  // 2Q = (Xd, Yd, Zd);  on the curve scaled by c = Zd it is the affine point (Xd, Yd)
+    fe c2, c3;
+    fe_sqr(c2, D.z);
+    fe_mul(c3, c2, D.z);
+    ge d_aff, q1;
+    d_aff.x = D.x;
+    d_aff.y = D.y;
+    fe_mul(q1.x, Q.x, c2);  // Q on the scaled curve
+    fe_mul(q1.y, Q.y, c3);
+    gej_set_ge(acc, q1);
+    fe_to_words(tab[0].x, q1.x);
+    fe_to_words(tab[0].y, q1.y);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int k = 1; k < 8; k++) {
+        fe h;
+        gej_add_ge(acc, acc, d_aff, &h);  // (2k+1)Q ; never exceptional for a point of prime order > 15
+        fe_to_words(tab[k].x, acc.x);
+        fe_to_words(tab[k].y, acc.y);
+        fe_to_words(tab[k].h, h);
+    }
+    fe_mul(zc, acc.z, D.z);
+    // bring entries 6..0 to the Z of entry 7:  ratio_k = prod_{j=k+1..7} h_j
+    fe zr;
+    fe_from_words(zr, tab[7].h);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int k = 6; k >= 0; k--) {
+        fe zr2, zr3, t;
+        fe_sqr(zr2, zr);
+        fe_mul(zr3, zr2, zr);
+        fe_from_words(t, tab[k].x);
+        fe_mul(t, t, zr2);
+        fe_to_words(tab[k].x, t);
+        fe_from_words(t, tab[k].y);
+        fe_mul(t, t, zr3);
+        fe_to_words(tab[k].y, t);
+        if (k > 0) {
+            fe_from_words(t, tab[k].h);
+            fe_mul(zr, zr, t);
+        }
+    }
+}
+
+// fetch table entry for window value v (0..15) of a scalar with sign `sneg`; lam -> apply beta
+SV_HD void qtable_fetch(ge& p, const qtab_entry* tab, u32 v, u32 sneg, bool lam) {
+    u32 dneg = (v < 8) ? 1u : 0u;
+    u32 idx = dneg ? (7u - v) : (v - 8u);
+    fe_from_words(p.x, tab[idx].x);
+    fe_from_words(p.y, tab[idx].y);
+    if (lam) {
+        fe beta;
+        SV_UNROLL
+        for (int i = 0; i < 8; i++) beta.v[i] = GE_BETA[i];
+        fe_mul(p.x, p.x, beta);
+    }
+    if (dneg ^ sneg) fe_neg(p.y, p.y);
+}
+
+// R = u1*G + u2*Q in true Jacobian coordinates.
+SV_HD void ecmult_uniform(gej& R, const sv_work& w, const ge& Q, const ge_mem* gtab, qtab_entry* tab) {
+    fe zc;
+    qtable_build(tab, zc, Q);
+    u32 m1[5], m2[5];
+    SV_UNROLL
+    for (int i = 0; i < 5; i++) { m1[i] = w.k1[i]; m2[i] = w.k2[i]; }
+    u32 s1 = m1[4] >> 31, s2 = m2[4] >> 31;
+    m1[4] &= 0x7FFFFFFFu;
+    m2[4] &= 0x7FFFFFFFu;
+    ge p;
+    // top window (i = 32): digit = 2*(mag >> 129) + 1, always positive
+    {
+        u32 v1 = (m1[4] >> 1) & 7u, v2 = (m2[4] >> 1) & 7u;
+        qtable_fetch(p, tab, v1 + 8u, s1, false);
+        gej_set_ge(R, p);
+        qtable_fetch(p, tab, v2 + 8u, s2, true);
+        gej_add_ge(R, R, p);
+    }
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int i = 31; i >= 0; i--) {
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+        for (int j = 0; j < 4; j++) gej_double(R, R);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+        for (int half = 0; half < 2; half++) {
+            u32 v = half ? window4(m2, i) : window4(m1, i);
+            qtable_fetch(p, tab, v, half ? s2 : s1, half != 0);
+            gej_add_ge(R, R, p);
+        }
+    }
+    // leave the scaled curve: true Z = Z * zc
+    fe_mul(R.z, R.z, zc);
+    // fixed-base comb
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int row = 0; row < 16; row++) {
+        int d = w.gd[row];
+        if (d != 0) {
+            u32 a = (u32)(d < 0 ? -d : d);
+            ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
+            if (d < 0) fe_neg(p.y, p.y);
+            gej_add_ge(R, R, p);
+        }
+    }
+}
+
+// final comparison, ECDSA: x(R) mod n == r without leaving Jacobian coordinates
+// (ecdsa_impl.h:229-264; secp256k1_gej_eq_x_var group_impl.h:396-404)
+SV_HD u32 ecdsa_final(const gej& R, const u8* sig64, u32 flags) {
+    if (R.inf) return 0;
+    fe xr, zz, t;
+    fe_set_b32(xr, sig64);  // r < n < p
+    fe_sqr(zz, R.z);
+    fe_mul(t, xr, zz);
+    if (fe_equal(t, R.x)) return 1;
+    if (flags & SV_WF_R_PLUS_N) {
+        fe nn;
+        SV_UNROLL
+        for (int i = 0; i < 8; i++) nn.v[i] = SC_N[i];
+        u256_add(xr.v, xr.v, nn.v);  // r + n < p: no wrap
+        fe_mul(t, xr, zz);
+        if (fe_equal(t, R.x)) return 1;
+    }
+    return 0;
+}
+
+// final comparison, BIP-340: R finite, y(R) even, x(R) == r  (main_impl.h:255-264)
+SV_HD u32 schnorr_final(const gej& R, const u8* sig64) {
+    if (R.inf) return 0;
+    fe zi, rx;
+    ge a;
+    fe_inv(zi, R.z);
+    ge_set_gej_zinv(a, R, zi);
+    fe_normalize(a.y);
+    if (fe_is_odd(a.y)) return 0;
+    fe_set_b32(rx, sig64);
+    return fe_equal(rx, a.x) ? 1u : 0u;
+}
+
+// whole curve side for one item
+SV_HD u32 verify_curve_side(int kind, const sv_work& w, const u8* key, const u8* sig64, const ge_mem* gtab,
+                            qtab_entry* tab) {
+    if (!(w.flags & SV_WF_VALID)) return 0;
+    ge Q;
+    if (!key_decode(Q, kind, key)) return 0;
+    gej R;
+    ecmult_uniform(R, w, Q, gtab, tab);
+    return (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, w.flags);
+}
+
+// =================================================================================================
+// fixed-base table construction (K4)
+// =================================================================================================
+
+// bases[i] = 2^(16 i) * G, i = 0..15 (one thread)
+SV_HD void gtable_make_bases(ge_mem* bases) {
+    ge g;
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) { g.x.v[i] = GE_GX[i]; g.y.v[i] = GE_GY[i]; }
+    for (int i = 0; i < 16; i++) {
+        ge_to_mem(&bases[i], g);
+        gej j;
+        gej_set_ge(j, g);
+        for (int k = 0; k < 16; k++) gej_double(j, j);
+        fe zi;
+        fe_inv(zi, j.z);
+        ge_set_gej_zinv(g, j, zi);
+        fe_normalize(g.x);
+        fe_normalize(g.y);
+    }
+}
+// table entry e (0 <= e < SV_GT_ENTRIES): row = min(e / 32768, 15), d = e - row*32768 + 1; value d * bases[row]
+SV_HD void gtable_make_entry(ge_mem* table, const ge_mem* bases, u32 e) {
+    u32 row = e / SV_GT_ROW;
+    if (row > 15) row = 15;
+    u32 d = e - row * SV_GT_ROW + 1;  // 1 .. 65536
+    ge b;
+    ge_from_mem(b, &bases[row]);
+    gej acc;
+    acc.inf = 1;
+    fe_set_zero(acc.x);
+    fe_set_zero(acc.y);
+    fe_set_zero(acc.z);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int bit = 16; bit >= 0; bit--) {
+        if (!acc.inf) gej_double(acc, acc);
+        if ((d >> bit) & 1u) gej_add_ge(acc, acc, b);
+    }
+    fe zi;
+    ge a;
+    fe_inv(zi, acc.z);
+    ge_set_gej_zinv(a, acc, zi);
+    fe_normalize(a.x);
+    fe_normalize(a.y);
+    ge_to_mem(&table[e], a);
+}

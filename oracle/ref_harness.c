@@ -1,0 +1,154 @@
+/*
+ * oracle/ref_harness.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Thin batch harness over the UNMODIFIED reference implementation (libsecp256k1-zkp as
+ * vendored by the reference at external/libwally-core/src/secp256k1/, and CCAN sha256 at
+ * ccan/ccan/crypto/sha256/sha256.c).  The reference sources are compiled where they lie
+ * under /root/reference by oracle/Makefile; only this file (our own code, public API calls
+ * only) lives in the repo.  Output: oracle/_ref/libsecp_ref.so.
+ *
+ * What each entry point times/checks is exactly the per-item sequence BASELINE.md §3 names:
+ *   ECDSA   : secp256k1_ec_pubkey_parse + secp256k1_ecdsa_signature_parse_compact +
+ *             secp256k1_ecdsa_verify            (reference: secp256k1.c:270,377,442)
+ *   Schnorr : secp256k1_xonly_pubkey_parse + secp256k1_schnorrsig_verify(msglen 32)
+ *             (reference: modules/extrakeys/main_impl.h:23, modules/schnorrsig/main_impl.h:219)
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <secp256k1.h>
+#include <secp256k1_extrakeys.h>
+#include <secp256k1_schnorrsig.h>
+
+static secp256k1_context *g_ctx;
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+static void ctx_init(void) { g_ctx = secp256k1_context_create(SECP256K1_CONTEXT_NONE); }
+static secp256k1_context *ctx(void) { pthread_once(&g_once, ctx_init); return g_ctx; }
+
+typedef struct {
+    int kind; /* 0 ecdsa33, 1 ecdsa65(04|x|y given as 64 raw bytes), 2 schnorr */
+    const uint8_t *msg, *pub, *sig;
+    size_t lo, hi;
+    uint8_t *out;
+} job_t;
+
+static int verify_ecdsa(const uint8_t *msg32, const uint8_t *pub, size_t publen, const uint8_t *sig64) {
+    secp256k1_pubkey pk;
+    secp256k1_ecdsa_signature s;
+    if (!secp256k1_ec_pubkey_parse(ctx(), &pk, pub, publen)) return 0;
+    if (!secp256k1_ecdsa_signature_parse_compact(ctx(), &s, sig64)) return 0;
+    return secp256k1_ecdsa_verify(ctx(), &s, msg32, &pk);
+}
+
+static int verify_schnorr(const uint8_t *msg32, const uint8_t *xonly32, const uint8_t *sig64) {
+    secp256k1_xonly_pubkey pk;
+    if (!secp256k1_xonly_pubkey_parse(ctx(), &pk, xonly32)) return 0;
+    return secp256k1_schnorrsig_verify(ctx(), sig64, msg32, 32, &pk);
+}
+
+static void *worker(void *arg) {
+    job_t *j = (job_t *)arg;
+    for (size_t i = j->lo; i < j->hi; i++) {
+        if (j->kind == 0) {
+            j->out[i] = (uint8_t)verify_ecdsa(j->msg + 32 * i, j->pub + 33 * i, 33, j->sig + 64 * i);
+        } else if (j->kind == 1) {
+            uint8_t pk65[65];
+            pk65[0] = 4;
+            memcpy(pk65 + 1, j->pub + 64 * i, 64);
+            j->out[i] = (uint8_t)verify_ecdsa(j->msg + 32 * i, pk65, 65, j->sig + 64 * i);
+        } else {
+            j->out[i] = (uint8_t)verify_schnorr(j->msg + 32 * i, j->pub + 32 * i, j->sig + 64 * i);
+        }
+    }
+    return NULL;
+}
+
+static void run(int kind, const uint8_t *msg, const uint8_t *pub, const uint8_t *sig, size_t n,
+                uint8_t *out, int nthreads) {
+    (void)ctx();
+    if (nthreads < 1) nthreads = 1;
+    if ((size_t)nthreads > n && n > 0) nthreads = (int)n;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    job_t *jobs = (job_t *)malloc(sizeof(job_t) * (size_t)nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (job_t){kind, msg, pub, sig, n * (size_t)t / (size_t)nthreads,
+                          n * (size_t)(t + 1) / (size_t)nthreads, out};
+        if (nthreads == 1) worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, worker, &jobs[t]);
+    }
+    if (nthreads > 1)
+        for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th);
+    free(jobs);
+}
+
+/* SoA inputs: msg[n][32], pub[n][33|64|32], sig[n][64]; out[n] = 0/1. */
+void ref_ecdsa_verify_batch(const uint8_t *msg, const uint8_t *pub33, const uint8_t *sig, size_t n,
+                            uint8_t *out, int nthreads) { run(0, msg, pub33, sig, n, out, nthreads); }
+void ref_ecdsa_verify_batch_xy(const uint8_t *msg, const uint8_t *pubxy64, const uint8_t *sig, size_t n,
+                               uint8_t *out, int nthreads) { run(1, msg, pubxy64, sig, n, out, nthreads); }
+void ref_schnorr_verify_batch(const uint8_t *msg, const uint8_t *xonly32, const uint8_t *sig, size_t n,
+                              uint8_t *out, int nthreads) { run(2, msg, xonly32, sig, n, out, nthreads); }
+
+/* ---- helpers for fixture generation (tests only) ---- */
+int ref_ecdsa_sign(const uint8_t *seckey32, const uint8_t *msg32, uint8_t *sig64_out) {
+    secp256k1_ecdsa_signature s;
+    if (!secp256k1_ecdsa_sign(ctx(), &s, msg32, seckey32, NULL, NULL)) return 0;
+    return secp256k1_ecdsa_signature_serialize_compact(ctx(), sig64_out, &s);
+}
+int ref_pubkey_create(const uint8_t *seckey32, uint8_t *pub33_out, uint8_t *pubxy64_out) {
+    secp256k1_pubkey pk;
+    uint8_t u[65];
+    size_t l = 33;
+    if (!secp256k1_ec_pubkey_create(ctx(), &pk, seckey32)) return 0;
+    secp256k1_ec_pubkey_serialize(ctx(), pub33_out, &l, &pk, SECP256K1_EC_COMPRESSED);
+    l = 65;
+    secp256k1_ec_pubkey_serialize(ctx(), u, &l, &pk, SECP256K1_EC_UNCOMPRESSED);
+    if (pubxy64_out) memcpy(pubxy64_out, u + 1, 64);
+    return 1;
+}
+int ref_schnorr_sign(const uint8_t *seckey32, const uint8_t *msg32, uint8_t *sig64_out, uint8_t *xonly32_out) {
+    secp256k1_keypair kp;
+    secp256k1_xonly_pubkey xo;
+    if (!secp256k1_keypair_create(ctx(), &kp, seckey32)) return 0;
+    if (!secp256k1_schnorrsig_sign32(ctx(), sig64_out, msg32, &kp, NULL)) return 0;
+    secp256k1_keypair_xonly_pub(ctx(), &xo, NULL, &kp);
+    return secp256k1_xonly_pubkey_serialize(ctx(), xonly32_out, &xo);
+}
+/* DER -> compact (returns 0 if the reference's strict DER parser rejects it). */
+int ref_sig_der_to_compact(const uint8_t *der, size_t len, uint8_t *sig64_out) {
+    secp256k1_ecdsa_signature s;
+    if (!secp256k1_ecdsa_signature_parse_der(ctx(), &s, der, len)) return 0;
+    return secp256k1_ecdsa_signature_serialize_compact(ctx(), sig64_out, &s);
+}
+/* any SEC1 pubkey encoding -> 33-byte compressed + raw x|y */
+int ref_pubkey_convert(const uint8_t *in, size_t inlen, uint8_t *pub33_out, uint8_t *pubxy64_out) {
+    secp256k1_pubkey pk;
+    uint8_t u[65];
+    size_t l = 33;
+    if (!secp256k1_ec_pubkey_parse(ctx(), &pk, in, inlen)) return 0;
+    secp256k1_ec_pubkey_serialize(ctx(), pub33_out, &l, &pk, SECP256K1_EC_COMPRESSED);
+    l = 65;
+    secp256k1_ec_pubkey_serialize(ctx(), u, &l, &pk, SECP256K1_EC_UNCOMPRESSED);
+    memcpy(pubxy64_out, u + 1, 64);
+    return 1;
+}
+/* x*G serialised uncompressed-without-prefix (for the ecmult KAT and G-table checks) */
+int ref_scalar_base_mult(const uint8_t *scalar32, uint8_t *xy64_out) {
+    return ref_pubkey_create(scalar32, (uint8_t[33]){0}, xy64_out);
+}
+
+/* CCAN sha256 (reference: ccan/ccan/crypto/sha256/sha256.c:243) and bitcoin/shadouble.c:7 semantics */
+struct sha256 { union { uint32_t u32[8]; unsigned char u8[32]; } u; };
+void sha256(struct sha256 *sha, const void *p, size_t size);
+void ref_sha256(const uint8_t *p, size_t len, uint8_t *out32) {
+    struct sha256 h; sha256(&h, p, len); memcpy(out32, h.u.u8, 32);
+}
+void ref_sha256d(const uint8_t *p, size_t len, uint8_t *out32) {
+    struct sha256 h, h2; sha256(&h, p, len); sha256(&h2, &h, sizeof(h)); memcpy(out32, h2.u.u8, 32);
+}
+/* tagged hash as used by the reference (hash_impl.h secp256k1_sha256_initialize_tagged) */
+void ref_tagged_sha256(const uint8_t *tag, size_t taglen, const uint8_t *msg, size_t msglen, uint8_t *out32) {
+    secp256k1_tagged_sha256(ctx(), out32, tag, taglen, msg, msglen);
+}

@@ -1,0 +1,170 @@
+// tests/host_emul/emul.cpp — TEST-ONLY build of the kernel source for the host.
+//
+// The engine's device headers (lightning_b200/csrc/*.cuh) are written against a handful of
+// 256-bit primitives that have a portable uint64_t fallback next to their inline-PTX form.  This
+// translation unit compiles those very headers with g++ so that all logic above the primitives
+// (field/scalar reduction, addition chains, group law case analysis, GLV + window recoding, table
+// construction, accept/reject rules, SHA-256) can be differential-tested against the oracle on a
+// machine without a GPU.  It is NOT part of the product: libcln_sigverify.so never contains or
+// calls this code, and the engine has no CPU execution path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../lightning_b200/csrc/verify.cuh"
+
+static std::vector<ge_mem> g_table;
+static std::vector<ge_mem> g_bases(16);
+
+static void build_gtable_fast() {
+    if (!g_table.empty()) return;
+    gtable_make_bases(g_bases.data());
+    g_table.resize(SV_GT_ENTRIES);
+    // incremental: entry(row, d) = entry(row, d-1) + base, Jacobian, then one batched inversion per row
+    for (int row = 0; row < 16; row++) {
+        size_t cnt = (row == 15) ? 65536 : SV_GT_ROW;
+        size_t off = (size_t)row * SV_GT_ROW;
+        ge b;
+        ge_from_mem(b, &g_bases[row]);
+        std::vector<gej> pts(cnt);
+        gej acc;
+        gej_set_ge(acc, b);
+        pts[0] = acc;
+        for (size_t d = 1; d < cnt; d++) {
+            gej_add_ge(acc, acc, b);
+            pts[d] = acc;
+        }
+        std::vector<fe> pre(cnt);
+        pre[0] = pts[0].z;
+        for (size_t d = 1; d < cnt; d++) fe_mul(pre[d], pre[d - 1], pts[d].z);
+        fe inv;
+        fe_inv(inv, pre[cnt - 1]);
+        for (size_t d = cnt; d-- > 0;) {
+            fe zi;
+            if (d > 0) {
+                fe_mul(zi, inv, pre[d - 1]);
+                fe_mul(inv, inv, pts[d].z);
+            } else {
+                zi = inv;
+            }
+            ge a;
+            ge_set_gej_zinv(a, pts[d], zi);
+            fe_normalize(a.x);
+            fe_normalize(a.y);
+            ge_to_mem(&g_table[off + d], a);
+        }
+    }
+}
+
+extern "C" {
+
+void emul_fe_op(int op, const u32* a, const u32* b, u32* out) {
+    fe x, y, r;
+    memcpy(x.v, a, 32);
+    if (b) memcpy(y.v, b, 32); else fe_set_zero(y);
+    switch (op) {
+        case 0: fe_mul(r, x, y); break;
+        case 1: fe_sqr(r, x); break;
+        case 2: fe_add(r, x, y); break;
+        case 3: fe_sub(r, x, y); break;
+        case 4: fe_inv(r, x); break;
+        case 5: { bool ok = fe_sqrt(r, x); if (!ok) fe_set_zero(r); break; }
+        case 6: fe_neg(r, x); break;
+        case 7: fe_mul_small(r, x, y.v[0]); break;
+        default: fe_set_zero(r);
+    }
+    fe_normalize(r);
+    memcpy(out, r.v, 32);
+}
+// raw (un-normalised) result, to check the weak-form invariant value < 2^256 and congruence
+void emul_fe_op_raw(int op, const u32* a, const u32* b, u32* out) {
+    fe x, y, r;
+    memcpy(x.v, a, 32);
+    memcpy(y.v, b, 32);
+    switch (op) {
+        case 0: fe_mul(r, x, y); break;
+        case 2: fe_add(r, x, y); break;
+        case 3: fe_sub(r, x, y); break;
+        default: fe_set_zero(r);
+    }
+    memcpy(out, r.v, 32);
+}
+void emul_sc_op(int op, const u32* a, const u32* b, u32* out) {
+    sc x, y, r;
+    memcpy(x.v, a, 32);
+    if (b) memcpy(y.v, b, 32);
+    switch (op) {
+        case 0: sc_mul(r, x, y); break;
+        case 1: sc_inverse(r, x); break;
+        case 2: sc_add(r, x, y); break;
+        case 3: sc_negate(r, x); break;
+        default: memset(r.v, 0, 32);
+    }
+    memcpy(out, r.v, 32);
+}
+void emul_sc_reduce512(const u32* t16, u32* out) {
+    sc r;
+    sc_reduce512(r, t16);
+    memcpy(out, r.v, 32);
+}
+// GLV + recoding: returns k1[5],k2[5] (sign in bit 31 of limb 4) and gd[16]
+void emul_prepare(const u32* u1, const u32* u2, u32* k1, u32* k2, int* gd) {
+    sv_work w;
+    sc a, b;
+    memcpy(a.v, u1, 32);
+    memcpy(b.v, u2, 32);
+    sc_prepare_u2(w, b);
+    sc_prepare_u1(w, a);
+    memcpy(k1, w.k1, 20);
+    memcpy(k2, w.k2, 20);
+    memcpy(gd, w.gd, 64);
+}
+void emul_sha256d(const u8* p, size_t len, u8* out32) { sha256d_bytes(out32, p, len); }
+void emul_bip340_challenge(const u8* r32, const u8* px32, const u8* msg32, u8* out32) {
+    sha256_bip340_challenge(out32, r32, px32, msg32);
+}
+
+void emul_gtable_build(void) { build_gtable_fast(); }
+// entry computed the way the device kernel does it (double-and-add + Fermat), for cross-checking
+void emul_gtable_entry_device_algo(u32 e, u32* xy16) {
+    build_gtable_fast();
+    std::vector<ge_mem> one(SV_GT_ENTRIES > 0 ? 1 : 1);
+    // gtable_make_entry writes table[e]; give it a fake base pointer so that only slot e is touched
+    ge_mem slot;
+    gtable_make_entry(&slot - e, g_bases.data(), e);
+    memcpy(xy16, slot.x, 32);
+    memcpy(xy16 + 8, slot.y, 32);
+}
+void emul_gtable_get(u32 e, u32* xy16) {
+    build_gtable_fast();
+    memcpy(xy16, g_table[e].x, 32);
+    memcpy(xy16 + 8, g_table[e].y, 32);
+}
+
+// full verification of a batch, same data flow as the kernels (prep in groups of SV_PREP_BATCH)
+void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, size_t n, u8* out) {
+    build_gtable_fast();
+    size_t keylen = kind == SV_KIND_ECDSA33 ? 33 : (kind == SV_KIND_ECDSA_XY ? 64 : 32);
+    std::vector<sv_work> work(n);
+    if (kind == SV_KIND_SCHNORR) {
+        for (size_t i = 0; i < n; i++) schnorr_prep(work[i], sig + 64 * i, key + keylen * i, msg + 32 * i);
+    } else {
+        for (size_t base = 0; base < n; base += SV_PREP_BATCH) {
+            int cnt = (int)((n - base < SV_PREP_BATCH) ? (n - base) : SV_PREP_BATCH);
+            sc r[SV_PREP_BATCH], m[SV_PREP_BATCH], sv[SV_PREP_BATCH];
+            bool ok[SV_PREP_BATCH];
+            for (int j = 0; j < cnt; j++) {
+                sc s;
+                ok[j] = ecdsa_parse(r[j], s, m[j], sig + 64 * (base + j), msg + 32 * (base + j));
+                if (!ok[j]) { memset(s.v, 0, 32); s.v[0] = 1; }
+                sv[j] = s;
+            }
+            sc_batch_inverse(sv, cnt);
+            for (int j = 0; j < cnt; j++) ecdsa_finish_prep(work[base + j], ok[j], r[j], m[j], sv[j]);
+        }
+    }
+    qtab_entry tab[8];
+    for (size_t i = 0; i < n; i++)
+        out[i] = (u8)verify_curve_side(kind, work[i], key + keylen * i, sig + 64 * i, g_table.data(), tab);
+}
+}
