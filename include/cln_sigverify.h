@@ -1,0 +1,130 @@
+/*
+ * cln_sigverify.h — C ABI of the B200 batched secp256k1 verification engine (libcln_sigverify.so).
+ *
+ * This is the drop-in boundary behind Core Lightning's bitcoin/signature.h surface.  Plain C,
+ * plain pointers and sizes; no CUDA, torch or libsecp256k1 types appear in any signature.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the CLN tree):
+ *
+ *   sv_verify_host(SV_KIND_ECDSA_XY, ...)   check_signed_hash()          bitcoin/signature.c:174-192
+ *                                           (hash32, secp256k1_ecdsa_signature, struct pubkey)
+ *   sv_verify_host(SV_KIND_ECDSA33, ...)    check_signed_hash_nodeid()   common/node_id.c:72-80
+ *                                           (33-byte node_id decompressed per call, then as above)
+ *   sv_verify_host(SV_KIND_SCHNORR, ...)    check_schnorr_sig()          bitcoin/signature.c:408-430
+ *   sv_verify_host_raw(...)                 sha256_double() + the above  bitcoin/shadouble.c:7-11,
+ *                                           as used by gossipd/sigcheck.c:9-43, 45-115, 118-164 and,
+ *                                           with a BIP143 preimage as the span, check_tx_sig()
+ *                                           bitcoin/signature.c:194-221 (the per-HTLC loop of
+ *                                           channeld/channeld.c:2215-2232)
+ *   sv_sha256d_host(...)                    sha256_double()              bitcoin/shadouble.c:7-11
+ *   sv_pubkey_parse_host(...)               pubkey_from_der()            bitcoin/pubkey.c:14-24
+ *   sv_enqueue_* / sv_flush                 the deferral queue a batching caller (gossipd ingest,
+ *                                           SURVEY.md §8f N1) sits on; synchronous check_* = enqueue 1 + flush
+ *   sv_verify_device(...)                   same kernels on device-resident arrays (bench / multi-GPU)
+ *
+ * Verdict semantics are those of the reference, bit for bit, INCLUDING the parse-time rejects CLN
+ * performs before check_signed_hash (r >= n, s >= n: wire/fromwire.c:188-199; bad pubkey:
+ * bitcoin/pubkey.c:102-113): a verdict byte is 1 iff libsecp256k1 would parse the key, parse the
+ * signature and return 1 from secp256k1_ecdsa_verify / secp256k1_schnorrsig_verify.
+ *
+ * Error convention: a verification failure is verdict 0, never an error code.
+ * Engine failures (no device, CUDA error, out of memory) return a negative sv_status and leave the
+ * verdict buffer untouched; there is NO CPU fallback.  The check_* drop-in wrappers in
+ * cln_dropin.h abort() on engine failure, matching CLN's "internal error is fatal" style.
+ *
+ * Threading: one sv_ctx per thread/process (CLN daemons are single-threaded event loops).
+ */
+#ifndef CLN_SIGVERIFY_H
+#define CLN_SIGVERIFY_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sv_ctx sv_ctx;
+
+/* item kinds (layout of the key array; msg is always 32 bytes, sig always 64 bytes) */
+#define SV_KIND_ECDSA33 0  /* key = 33-byte SEC1 compressed (02/03 || x)           sig = r_be32 || s_be32 */
+#define SV_KIND_ECDSA_XY 1 /* key = 64 bytes x_be32 || y_be32 (pre-decompressed)   sig = r_be32 || s_be32 */
+#define SV_KIND_SCHNORR 2  /* key = 32-byte x-only (BIP-340)                        sig = R.x_be32 || s_be32 */
+
+typedef enum {
+    SV_OK = 0,
+    SV_ERR_NO_DEVICE = -1,
+    SV_ERR_CUDA = -2,
+    SV_ERR_NOMEM = -3,
+    SV_ERR_ARG = -4
+} sv_status;
+
+/* Create an engine on CUDA device `device` (ordinal).  Allocates the stream, builds the 34 MiB
+ * fixed-base table on the device (kernel K4) and the per-thread scratch.  */
+int sv_create(sv_ctx **out, int device);
+void sv_destroy(sv_ctx *ctx);
+/* last error text for this context (or for a failed sv_create when ctx == NULL) */
+const char *sv_last_error(const sv_ctx *ctx);
+/* size of the key element for a kind (33 / 64 / 32), or 0 */
+size_t sv_key_size(int kind);
+
+/* ---- synchronous batch verification, HOST buffers (SoA): msg32[n][32], key[n][keysize], sig64[n][64];
+ *      verdicts[n] receives 0/1.  Copies in, runs the kernels, copies out, returns when done. ---- */
+int sv_verify_host(sv_ctx *ctx, int kind, const uint8_t *msg32, const uint8_t *key, const uint8_t *sig64,
+                   size_t n, uint8_t *verdicts);
+
+/* ---- same, but the message hash is computed on the device: item i signs
+ *      SHA256d(data[off[i] .. off[i]+len[i])).  Several items may share one span (the four
+ *      signatures of a channel_announcement do). ---- */
+int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_len, const uint64_t *off,
+                       const uint32_t *len, const uint8_t *key, const uint8_t *sig64, size_t n,
+                       uint8_t *verdicts);
+
+/* ---- DEVICE buffers (same SoA layout, device pointers); asynchronous on `stream`
+ *      (a cudaStream_t passed as void*; NULL = the context's own stream).  d_verdicts[n] bytes;
+ *      d_bitmap, if non-NULL, receives ceil(n/32) little-endian 32-bit words, bit i%32 of word i/32. ---- */
+int sv_verify_device(sv_ctx *ctx, int kind, const void *d_msg32, const void *d_key, const void *d_sig64, size_t n,
+                     void *d_verdicts, void *d_bitmap, void *stream);
+int sv_sync(sv_ctx *ctx, void *stream);
+
+/* ---- deferral queue: enqueue returns the item's index in the pending batch; sv_flush verifies all
+ *      pending items of every kind and writes one verdict byte per item in enqueue order. ---- */
+long sv_enqueue(sv_ctx *ctx, int kind, const uint8_t msg32[32], const uint8_t *key, const uint8_t sig64[64]);
+size_t sv_pending(const sv_ctx *ctx);
+int sv_flush(sv_ctx *ctx, uint8_t *verdicts, size_t capacity);
+
+/* ---- helpers of the bitcoin/ surface that are pure functions of bytes ---- */
+/* out32[i] = SHA256d(data[off[i]..off[i]+len[i]))   (bitcoin/shadouble.c:7) */
+int sv_sha256d_host(sv_ctx *ctx, const uint8_t *data, size_t data_len, const uint64_t *off, const uint32_t *len,
+                    size_t n, uint8_t *out32);
+/* pubkey_from_der semantics for a batch: key33[n][33] -> xy64[n][64] (x||y big-endian), ok[n] = 0/1 */
+int sv_pubkey_parse_host(sv_ctx *ctx, const uint8_t *key33, size_t n, uint8_t *xy64, uint8_t *ok);
+
+/* ---- synthetic workload generator (benchmark / test support; NOT constant time, no secrets):
+ *      item i gets secret key and nonce derived from (seed, i); writes msg32, key (per kind) and a
+ *      VALID low-S ECDSA / BIP-340 signature to device arrays. ---- */
+int sv_synth_device(sv_ctx *ctx, int kind, uint64_t seed, size_t n, void *d_msg32, void *d_key, void *d_sig64,
+                    void *stream);
+
+/* ---- introspection for the benchmark ---- */
+typedef struct {
+    int device;
+    int sm_count;
+    int main_block;       /* threads per CTA of the curve-side kernel */
+    int main_grid;        /* CTAs */
+    int main_regs;        /* registers per thread (cudaFuncGetAttributes) */
+    size_t gtable_bytes;
+    size_t scratch_bytes;
+    unsigned long long launches; /* kernels launched by this context so far */
+} sv_info;
+int sv_get_info(const sv_ctx *ctx, sv_info *info);
+
+/* integer-pipe roofline probe: runs a dependent-chain IMAD.WIDE.U32 microbenchmark and returns the
+ * achieved 32x32->64 multiply-accumulates per second on this device (the roofline denominator
+ * SURVEY.md §8d asks to be measured, not assumed). */
+int sv_probe_imad_peak(sv_ctx *ctx, double *imad_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

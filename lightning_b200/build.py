@@ -1,0 +1,80 @@
+"""Build recipes for the engine (nvcc, sm_100a only) and for the test-side artefacts.
+
+Everything is built IN-TREE so that the shared objects travel with a gpurun snapshot:
+  lightning_b200/libcln_sigverify.so   the product (CUDA kernels + C ABI)            [nvcc]
+  tests/host_emul/libemul.so           kernel headers compiled for the host, tests only [g++]
+  oracle/libsecp_port.so               the plain-C restatement oracle                 [gcc]
+  oracle/_ref/libsecp_ref.so           the unmodified reference, when /root/reference exists [gcc]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "lightning_b200", "csrc")
+LIB = os.path.join(ROOT, "lightning_b200", "libcln_sigverify.so")
+EMUL = os.path.join(ROOT, "tests", "host_emul", "libemul.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(d, exts):
+    out = []
+    for base, _, files in os.walk(d):
+        out += [os.path.join(base, f) for f in files if f.endswith(exts)]
+    return out
+
+
+def build_engine(force=False, verbose=False, extra_flags=()):
+    srcs = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "cln_sigverify.h")]
+    if not force and _newer(LIB, srcs):
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + [
+        "-o", LIB, os.path.join(CSRC, "engine.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB
+
+
+def build_host_emul(force=False):
+    src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
+    srcs = _sources(CSRC, (".cuh",)) + [src]
+    if not force and _newer(EMUL, srcs):
+        return EMUL
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unused-function", "-o", EMUL, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ (host_emul) failed:\n" + r.stdout + r.stderr)
+    return EMUL
+
+
+def build_oracle():
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+
+
+def build_all(force=False, verbose=False):
+    build_engine(force=force, verbose=verbose)
+    build_host_emul(force=force)
+    build_oracle()
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built:", LIB)

@@ -20,7 +20,9 @@
 #define SV_HD_NOINLINE static
 #endif
 
-#if defined(__CUDA_ARCH__)
+// all SV_HD functions are __device__-only under nvcc, so the PTX path is selected by the compiler,
+// not by the compilation pass (nvcc's host pass merely parses these bodies)
+#if defined(__CUDACC__)
 #define SV_DEVICE_CODE 1
 #define SV_UNROLL _Pragma("unroll")
 #else

@@ -1,0 +1,665 @@
+// engine.cu — kernels and C ABI of libcln_sigverify.so (sm_100a).
+//
+// Kernels (SURVEY.md §2.3 naming):
+//   K4  k_gtable_bases / k_gtable_fill   fixed-base comb table d * 2^(16 i) * G, built once per context
+//   K3  k_sha256d                        SHA-256d of message spans (gossip tails, BIP143 preimages)
+//   K1a k_prep_ecdsa                     scalar side of ECDSA (16 signatures per thread, one s^-1 exponentiation)
+//   K2a k_prep_schnorr                   scalar side of BIP-340 (tagged challenge hash, -e, recoding)
+//   K1b/K2b k_main<kind>                 curve side: thread per verification, persistent grid
+//       k_pack_bitmap                    verdict bytes -> 1 bit per verification (ballot)
+//       k_pubkey_parse                   batched pubkey_from_der
+//       k_synth                          synthetic signed workload generator (benchmarks/tests)
+//       k_probe_*                        integer-pipe microbenchmarks (roofline denominator)
+//
+// There is no host implementation of any of the arithmetic in this library: every entry point either
+// runs the kernels or fails with an error code.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cln_sigverify.h"
+#include "verify.cuh"
+
+#ifndef SV_MAIN_BLOCK
+#define SV_MAIN_BLOCK 128
+#endif
+#ifndef SV_MAIN_MINB
+#define SV_MAIN_MINB 4
+#endif
+
+// -------------------------------------------------------------------------------------------------
+// kernels
+// -------------------------------------------------------------------------------------------------
+__global__ void k_gtable_bases(ge_mem* bases) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) gtable_make_bases(bases);
+}
+__global__ void __launch_bounds__(128) k_gtable_fill(ge_mem* table, const ge_mem* bases) {
+    u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < SV_GT_ENTRIES) gtable_make_entry(table, bases, e);
+}
+
+__global__ void __launch_bounds__(128) k_sha256d(const u8* data, const u64* off, const u32* len, size_t n, u8* out32) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sha256d_bytes(out32 + 32 * i, data + off[i], len[i]);
+}
+
+// scalar side, ECDSA.  Each thread owns SV_PREP_BATCH consecutive signatures so that the single
+// Fermat exponentiation mod n is amortised by Montgomery's trick (3 mults per signature instead of ~330).
+__global__ void __launch_bounds__(64) k_prep_ecdsa(const u8* msg, const u8* sig, size_t n, sv_work* work) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t base = t * SV_PREP_BATCH;
+    if (base >= n) return;
+    int cnt = (int)((n - base < SV_PREP_BATCH) ? (n - base) : SV_PREP_BATCH);
+    sc sv[SV_PREP_BATCH];
+    u32 okmask = 0;
+#pragma unroll 1
+    for (int j = 0; j < SV_PREP_BATCH; j++) {
+        sc r, s, m;
+        bool ok = false;
+        if (j < cnt) ok = ecdsa_parse(r, s, m, sig + 64 * (base + j), msg + 32 * (base + j));
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s.v[k] = (k == 0);
+        }
+        okmask |= (ok ? 1u : 0u) << j;
+        sv[j] = s;
+    }
+    sc_batch_inverse(sv, SV_PREP_BATCH);
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+        sc r, s, m;
+        (void)ecdsa_parse(r, s, m, sig + 64 * (base + j), msg + 32 * (base + j));
+        sv_work w;
+        ecdsa_finish_prep(w, (okmask >> j) & 1u, r, m, sv[j]);
+        work[base + j] = w;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_prep_schnorr(const u8* msg, const u8* key, const u8* sig, size_t n,
+                                                      sv_work* work) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sv_work w;
+    schnorr_prep(w, sig + 64 * i, key + 32 * i, msg + 32 * i);
+    work[i] = w;
+}
+
+// curve side: one thread per verification, persistent grid-stride loop.  Per-thread odd-multiples
+// table lives in an HBM/L2-resident scratch slab (768 B per thread, 64-byte entries read with LDG.128).
+template <int KIND>
+__global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
+    k_main(const sv_work* __restrict__ work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
+           const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict) {
+    const size_t keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    qtab_entry* tab = scratch + tid * 8;
+    for (size_t i = tid; i < n; i += stride) {
+        verdict[i] = (u8)verify_curve_side(KIND, work + i, key + keylen * i, sig + 64 * i, gtab, tab);
+    }
+}
+
+__global__ void k_pack_bitmap(const u8* verdict, size_t n, u32* bitmap) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 v = (i < n) ? (verdict[i] != 0) : 0u;
+    u32 b = __ballot_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0 && i < n) bitmap[i >> 5] = b;
+}
+
+__global__ void __launch_bounds__(128) k_pubkey_parse(const u8* key33, size_t n, u8* xy64, u8* okout) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge Q;
+    bool ok = key_decode(Q, SV_KIND_ECDSA33, key33 + 33 * i);
+    if (ok) {
+        fe_get_b32(xy64 + 64 * i, Q.x);
+        fe_get_b32(xy64 + 64 * i + 32, Q.y);
+    } else {
+        for (int k = 0; k < 64; k++) xy64[64 * i + k] = 0;
+    }
+    okout[i] = ok;
+}
+
+// ---- synthetic workload generator ---------------------------------------------------------------
+SV_D void synth_hash(u8 out[32], u64 seed, u64 idx, u32 tag) {
+    u8 buf[20];
+    for (int k = 0; k < 8; k++) { buf[k] = (u8)(seed >> (8 * k)); buf[8 + k] = (u8)(idx >> (8 * k)); }
+    for (int k = 0; k < 4; k++) buf[16 + k] = (u8)(tag >> (8 * k));
+    u32 st[8];
+    sha256_bytes(st, buf, 20);
+    for (int k = 0; k < 8; k++) {
+        out[4 * k] = (u8)(st[k] >> 24); out[4 * k + 1] = (u8)(st[k] >> 16);
+        out[4 * k + 2] = (u8)(st[k] >> 8); out[4 * k + 3] = (u8)st[k];
+    }
+}
+// k*G (affine, normalised) with the comb table
+SV_D void synth_base_mult(ge& out, const sc& k, const ge_mem* gtab) {
+    sv_work w;
+    sc_prepare_u1(w, k);
+    gej R;
+    R.inf = 1;
+    fe_set_zero(R.x); fe_set_zero(R.y); fe_set_zero(R.z);
+#pragma unroll 1
+    for (int row = 0; row < 16; row++) {
+        int d = w.gd[row];
+        if (d != 0) {
+            ge p;
+            u32 a = (u32)(d < 0 ? -d : d);
+            ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
+            if (d < 0) fe_neg(p.y, p.y);
+            gej_add_ge(R, R, p);
+        }
+    }
+    fe zi;
+    fe_inv(zi, R.z);
+    ge_set_gej_zinv(out, R, zi);
+    fe_normalize(out.x);
+    fe_normalize(out.y);
+}
+template <int KIND>
+__global__ void __launch_bounds__(128) k_synth(u64 seed, size_t n, const ge_mem* gtab, u8* msg, u8* key, u8* sig) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u8 h[32];
+    sc d, k, m, one;
+#pragma unroll
+    for (int q = 0; q < 8; q++) one.v[q] = (q == 0);
+    synth_hash(h, seed, i, 1);
+    sc_set_b32(d, h, nullptr);
+    if (sc_is_zero(d)) d = one;
+    synth_hash(h, seed, i, 2);
+    sc_set_b32(k, h, nullptr);
+    if (sc_is_zero(k)) k = one;
+    synth_hash(h, seed, i, 3);
+    for (int q = 0; q < 32; q++) msg[32 * i + q] = h[q];
+    sc_set_b32(m, h, nullptr);
+    ge P, R;
+    synth_base_mult(P, d, gtab);
+    synth_base_mult(R, k, gtab);
+    if (KIND == SV_KIND_SCHNORR) {
+        // BIP-340 signing equation with even-y P and R: s = k + e*d
+        if (fe_is_odd(P.y)) sc_negate(d, d);
+        if (fe_is_odd(R.y)) sc_negate(k, k);
+        u8 rx[32], px[32], e32[32];
+        fe_get_b32(rx, R.x);
+        fe_get_b32(px, P.x);
+        sha256_bip340_challenge(e32, rx, px, h);
+        sc e, s;
+        sc_set_b32(e, e32, nullptr);
+        sc_mul(s, e, d);
+        sc_add(s, s, k);
+        for (int q = 0; q < 32; q++) { key[32 * i + q] = px[q]; sig[64 * i + q] = rx[q]; }
+        sc_get_b32(sig + 64 * i + 32, s);
+    } else {
+        // ECDSA: r = x(kG) mod n, s = (m + r d)/k, normalised to low S
+        u8 rx[32];
+        fe_get_b32(rx, R.x);
+        sc r, s, kinv;
+        sc_set_b32(r, rx, nullptr);
+        sc_inverse(kinv, k);
+        sc_mul(s, r, d);
+        sc_add(s, s, m);
+        sc_mul(s, s, kinv);
+        if (sc_is_high(s)) sc_negate(s, s);
+        sc_get_b32(sig + 64 * i, r);
+        sc_get_b32(sig + 64 * i + 32, s);
+        if (KIND == SV_KIND_ECDSA33) {
+            key[33 * i] = fe_is_odd(P.y) ? 3 : 2;
+            fe_get_b32(key + 33 * i + 1, P.x);
+        } else {
+            fe_get_b32(key + 64 * i, P.x);
+            fe_get_b32(key + 64 * i + 32, P.y);
+        }
+    }
+}
+
+// ---- integer-pipe probes ------------------------------------------------------------------------
+// mode 0: independent IMAD.WIDE.U32 accumulations (8 chains/thread)   -> multiply-accumulates/s
+// mode 1: carry-chained IMAD.WIDE.U32.X rows exactly as u256_mul_wide issues them
+// mode 2: fe_mul throughput (field multiplications/s)   mode 3: fe_sqr throughput
+__global__ void __launch_bounds__(256) k_probe(int mode, int iters, u32* sink) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 0) {
+        u64 a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+        u32 x = t * 2654435761u + 12345u, y = t ^ 0x9E3779B9u;
+#pragma unroll 1
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\t"
+                             "mad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
+                             "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
+                             "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                             : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7)
+                             : "r"(x), "r"(y));
+            }
+        }
+        u64 s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+        if (s == 0x1234567ull) sink[0] = (u32)s;
+    } else if (mode == 1) {
+        u32 E[8], O[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { E[k] = t + k; O[k] = t * 3 + k; }
+        u32 a0 = t | 1, a1 = t ^ 0xABCDEFu, a2 = t * 7 + 1, a3 = ~t, b = t * 2654435761u;
+        u32 cs = 0;
+#pragma unroll 1
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                cs += sv_cmad4(E, a0, a1, a2, a3, b);
+                cs += sv_cmad4(O, a1, a2, a3, a0, b);
+            }
+        }
+        u32 s = cs;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= E[k] ^ O[k];
+        if (s == 0x12345u) sink[0] = s;
+    } else {
+        fe a, b;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { a.v[k] = t * 2654435761u + k; b.v[k] = (t ^ 0x5bd1e995u) * (k + 3); }
+#pragma unroll 1
+        for (int i = 0; i < iters; i++) {
+            if (mode == 2) { fe_mul(a, a, b); fe_mul(b, b, a); }
+            else { fe_sqr(a, a); fe_sqr(b, b); }
+        }
+        u32 s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= a.v[k] ^ b.v[k];
+        if (s == 0x12345u) sink[0] = s;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// context
+// -------------------------------------------------------------------------------------------------
+struct sv_queue_item {
+    int kind;
+    u8 msg[32];
+    u8 key[64];
+    u8 sig[64];
+};
+
+struct sv_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    ge_mem* d_gtab;
+    ge_mem* d_bases;
+    qtab_entry* d_scratch;
+    size_t scratch_bytes;
+    int main_grid;
+    // growable device staging for the host-buffer entry points
+    size_t cap;  // items
+    u8 *d_msg, *d_key, *d_sig, *d_verdict;
+    sv_work* d_work;
+    size_t work_cap;
+    // raw-span staging
+    u8* d_data;
+    size_t data_cap;
+    u64* d_off;
+    u32* d_len;
+    size_t span_cap;
+    u32* d_sink;
+    unsigned long long launches;
+    std::vector<sv_queue_item> queue;
+    std::string err;
+};
+
+static std::string g_create_err;
+
+static int fail(sv_ctx* ctx, int code, const char* what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return fail(ctx, e__ == cudaErrorMemoryAllocation ? SV_ERR_NOMEM : SV_ERR_CUDA, #call, e__); \
+    } while (0)
+
+extern "C" size_t sv_key_size(int kind) {
+    return kind == SV_KIND_ECDSA33 ? 33 : kind == SV_KIND_ECDSA_XY ? 64 : kind == SV_KIND_SCHNORR ? 32 : 0;
+}
+extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+static int ensure_work(sv_ctx* ctx, size_t n) {
+    if (n <= ctx->work_cap) return SV_OK;
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    ctx->d_work = nullptr;
+    ctx->work_cap = 0;
+    CK(cudaMalloc(&ctx->d_work, n * sizeof(sv_work)));
+    ctx->work_cap = n;
+    return SV_OK;
+}
+static int ensure_staging(sv_ctx* ctx, size_t n) {
+    if (n <= ctx->cap) return SV_OK;
+    cudaFree(ctx->d_msg); cudaFree(ctx->d_key); cudaFree(ctx->d_sig); cudaFree(ctx->d_verdict);
+    ctx->d_msg = ctx->d_key = ctx->d_sig = ctx->d_verdict = nullptr;
+    ctx->cap = 0;
+    CK(cudaMalloc(&ctx->d_msg, n * 32));
+    CK(cudaMalloc(&ctx->d_key, n * 64));
+    CK(cudaMalloc(&ctx->d_sig, n * 64));
+    CK(cudaMalloc(&ctx->d_verdict, n));
+    ctx->cap = n;
+    return SV_OK;
+}
+
+extern "C" int sv_create(sv_ctx** out, int device) {
+    sv_ctx* ctx = nullptr;
+    if (!out) return SV_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, SV_ERR_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)", e);
+    if (device < 0 || device >= ndev) return fail(nullptr, SV_ERR_ARG, "bad device ordinal", cudaSuccess);
+    CK(cudaSetDevice(device));
+    ctx = new sv_ctx();
+    ctx->device = device;
+    ctx->cap = ctx->work_cap = ctx->data_cap = ctx->span_cap = 0;
+    ctx->d_msg = ctx->d_key = ctx->d_sig = ctx->d_verdict = ctx->d_data = nullptr;
+    ctx->d_work = nullptr; ctx->d_off = nullptr; ctx->d_len = nullptr;
+    ctx->launches = 0;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { int rc = fail(nullptr, SV_ERR_CUDA, "cudaGetDeviceProperties", e); delete ctx; return rc; }
+    ctx->sm_count = prop.multiProcessorCount;
+    int rc = SV_OK;
+    do {
+#define CK2(call) { cudaError_t e2 = (call); if (e2 != cudaSuccess) { rc = fail(nullptr, e2 == cudaErrorMemoryAllocation ? SV_ERR_NOMEM : SV_ERR_CUDA, #call, e2); break; } }
+        CK2(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK2(cudaMalloc(&ctx->d_gtab, (size_t)SV_GT_ENTRIES * sizeof(ge_mem)));
+        CK2(cudaMalloc(&ctx->d_bases, 16 * sizeof(ge_mem)));
+        CK2(cudaMalloc(&ctx->d_sink, 64));
+        int occ = 0;
+        CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_main<SV_KIND_ECDSA33>, SV_MAIN_BLOCK, 0));
+        if (occ < 1) occ = 1;
+        ctx->main_grid = ctx->sm_count * occ;
+        ctx->scratch_bytes = (size_t)ctx->main_grid * SV_MAIN_BLOCK * 8 * sizeof(qtab_entry);
+        CK2(cudaMalloc(&ctx->d_scratch, ctx->scratch_bytes));
+        k_gtable_bases<<<1, 32, 0, ctx->stream>>>(ctx->d_bases);
+        k_gtable_fill<<<(SV_GT_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_gtab, ctx->d_bases);
+        ctx->launches += 2;
+        CK2(cudaGetLastError());
+        CK2(cudaStreamSynchronize(ctx->stream));
+#undef CK2
+    } while (0);
+    if (rc != SV_OK) { sv_destroy(ctx); return rc; }
+    *out = ctx;
+    return SV_OK;
+}
+
+extern "C" void sv_destroy(sv_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_gtab); cudaFree(ctx->d_bases); cudaFree(ctx->d_scratch); cudaFree(ctx->d_sink);
+    cudaFree(ctx->d_msg); cudaFree(ctx->d_key); cudaFree(ctx->d_sig); cudaFree(ctx->d_verdict);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_data); cudaFree(ctx->d_off); cudaFree(ctx->d_len);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int sv_get_info(const sv_ctx* ctx, sv_info* info) {
+    if (!ctx || !info) return SV_ERR_ARG;
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_main<SV_KIND_ECDSA33>);
+    info->device = ctx->device;
+    info->sm_count = ctx->sm_count;
+    info->main_block = SV_MAIN_BLOCK;
+    info->main_grid = ctx->main_grid;
+    info->main_regs = fa.numRegs;
+    info->gtable_bytes = (size_t)SV_GT_ENTRIES * sizeof(ge_mem);
+    info->scratch_bytes = ctx->scratch_bytes;
+    info->launches = ctx->launches;
+    return SV_OK;
+}
+
+// launch prep + main on device-resident SoA arrays
+static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
+                         u8* d_verdict, u32* d_bitmap, cudaStream_t st) {
+    if (n == 0) return SV_OK;
+    int rc = ensure_work(ctx, n);
+    if (rc) return rc;
+    if (kind == SV_KIND_SCHNORR) {
+        k_prep_schnorr<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_work);
+    } else {
+        size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
+        k_prep_ecdsa<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_msg, d_sig, n, ctx->d_work);
+    }
+    size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
+    unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
+    if (kind == SV_KIND_ECDSA33)
+        k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+    else if (kind == SV_KIND_ECDSA_XY)
+        k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+    else
+        k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+    ctx->launches += 2;
+    if (d_bitmap) {
+        size_t nb = (n + 255) / 256;
+        k_pack_bitmap<<<(unsigned)nb, 256, 0, st>>>(d_verdict, n, d_bitmap);
+        ctx->launches += 1;
+    }
+    CK(cudaGetLastError());
+    return SV_OK;
+}
+
+extern "C" int sv_verify_device(sv_ctx* ctx, int kind, const void* d_msg32, const void* d_key, const void* d_sig64,
+                                size_t n, void* d_verdicts, void* d_bitmap, void* stream) {
+    if (!ctx || sv_key_size(kind) == 0 || (n && (!d_msg32 || !d_key || !d_sig64 || !d_verdicts))) return SV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    return launch_verify(ctx, kind, (const u8*)d_msg32, (const u8*)d_key, (const u8*)d_sig64, n, (u8*)d_verdicts,
+                         (u32*)d_bitmap, st);
+}
+
+extern "C" int sv_sync(sv_ctx* ctx, void* stream) {
+    if (!ctx) return SV_ERR_ARG;
+    CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : ctx->stream));
+    return SV_OK;
+}
+
+#ifndef SV_HOST_CHUNK
+#define SV_HOST_CHUNK (1u << 21)
+#endif
+
+extern "C" int sv_verify_host(sv_ctx* ctx, int kind, const uint8_t* msg32, const uint8_t* key, const uint8_t* sig64,
+                              size_t n, uint8_t* verdicts) {
+    size_t ks = sv_key_size(kind);
+    if (!ctx || ks == 0 || (n && (!msg32 || !key || !sig64 || !verdicts))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    size_t chunk = n < SV_HOST_CHUNK ? n : SV_HOST_CHUNK;
+    int rc = ensure_staging(ctx, chunk);
+    if (rc) return rc;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t c = (n - off < chunk) ? (n - off) : chunk;
+        CK(cudaMemcpyAsync(ctx->d_msg, msg32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_key, key + ks * off, ks * c, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_sig, sig64 + 64 * off, 64 * c, cudaMemcpyHostToDevice, ctx->stream));
+        rc = launch_verify(ctx, kind, ctx->d_msg, ctx->d_key, ctx->d_sig, c, ctx->d_verdict, nullptr, ctx->stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(verdicts + off, ctx->d_verdict, c, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SV_OK;
+}
+
+static int stage_spans(sv_ctx* ctx, const uint8_t* data, size_t data_len, const uint64_t* off, const uint32_t* len,
+                       size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (off[i] > data_len || (size_t)len[i] > data_len - off[i]) return fail(ctx, SV_ERR_ARG, "span out of range", cudaSuccess);
+    if (data_len > ctx->data_cap) {
+        cudaFree(ctx->d_data); ctx->d_data = nullptr; ctx->data_cap = 0;
+        CK(cudaMalloc(&ctx->d_data, data_len ? data_len : 1));
+        ctx->data_cap = data_len;
+    }
+    if (n > ctx->span_cap) {
+        cudaFree(ctx->d_off); cudaFree(ctx->d_len); ctx->d_off = nullptr; ctx->d_len = nullptr; ctx->span_cap = 0;
+        CK(cudaMalloc(&ctx->d_off, n * sizeof(u64)));
+        CK(cudaMalloc(&ctx->d_len, n * sizeof(u32)));
+        ctx->span_cap = n;
+    }
+    CK(cudaMemcpyAsync(ctx->d_data, data, data_len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_off, off, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_len, len, n * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    return SV_OK;
+}
+
+extern "C" int sv_verify_host_raw(sv_ctx* ctx, int kind, const uint8_t* data, size_t data_len, const uint64_t* off,
+                                  const uint32_t* len, const uint8_t* key, const uint8_t* sig64, size_t n,
+                                  uint8_t* verdicts) {
+    size_t ks = sv_key_size(kind);
+    if (!ctx || ks == 0 || (n && (!data || !off || !len || !key || !sig64 || !verdicts))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    rc = stage_spans(ctx, data, data_len, off, len, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_key, key, ks * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sig, sig64, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_sha256d<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_data, ctx->d_off, ctx->d_len, n, ctx->d_msg);
+    ctx->launches += 1;
+    rc = launch_verify(ctx, kind, ctx->d_msg, ctx->d_key, ctx->d_sig, n, ctx->d_verdict, nullptr, ctx->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(verdicts, ctx->d_verdict, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SV_OK;
+}
+
+extern "C" int sv_sha256d_host(sv_ctx* ctx, const uint8_t* data, size_t data_len, const uint64_t* off,
+                               const uint32_t* len, size_t n, uint8_t* out32) {
+    if (!ctx || (n && (!data || !off || !len || !out32))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    rc = stage_spans(ctx, data, data_len, off, len, n);
+    if (rc) return rc;
+    k_sha256d<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_data, ctx->d_off, ctx->d_len, n, ctx->d_msg);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out32, ctx->d_msg, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SV_OK;
+}
+
+extern "C" int sv_pubkey_parse_host(sv_ctx* ctx, const uint8_t* key33, size_t n, uint8_t* xy64, uint8_t* ok) {
+    if (!ctx || (n && (!key33 || !xy64 || !ok))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_key, key33, 33 * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_pubkey_parse<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_key, n, ctx->d_sig, ctx->d_verdict);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(xy64, ctx->d_sig, 64 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ok, ctx->d_verdict, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SV_OK;
+}
+
+// ---- deferral queue -----------------------------------------------------------------------------
+extern "C" long sv_enqueue(sv_ctx* ctx, int kind, const uint8_t msg32[32], const uint8_t* key, const uint8_t sig64[64]) {
+    size_t ks = sv_key_size(kind);
+    if (!ctx || ks == 0 || !msg32 || !key || !sig64) return SV_ERR_ARG;
+    sv_queue_item it;
+    it.kind = kind;
+    memcpy(it.msg, msg32, 32);
+    memset(it.key, 0, 64);
+    memcpy(it.key, key, ks);
+    memcpy(it.sig, sig64, 64);
+    ctx->queue.push_back(it);
+    return (long)ctx->queue.size() - 1;
+}
+extern "C" size_t sv_pending(const sv_ctx* ctx) { return ctx ? ctx->queue.size() : 0; }
+
+extern "C" int sv_flush(sv_ctx* ctx, uint8_t* verdicts, size_t capacity) {
+    if (!ctx || (!verdicts && !ctx->queue.empty())) return SV_ERR_ARG;
+    size_t total = ctx->queue.size();
+    if (capacity < total) return SV_ERR_ARG;
+    // segregate by kind so that warps stay homogeneous, verify, scatter verdicts back in enqueue order
+    for (int kind = 0; kind < 3; kind++) {
+        size_t ks = sv_key_size(kind);
+        std::vector<size_t> idx;
+        for (size_t i = 0; i < total; i++)
+            if (ctx->queue[i].kind == kind) idx.push_back(i);
+        if (idx.empty()) continue;
+        size_t m = idx.size();
+        std::vector<u8> msg(32 * m), key(ks * m), sig(64 * m), out(m);
+        for (size_t j = 0; j < m; j++) {
+            const sv_queue_item& it = ctx->queue[idx[j]];
+            memcpy(&msg[32 * j], it.msg, 32);
+            memcpy(&key[ks * j], it.key, ks);
+            memcpy(&sig[64 * j], it.sig, 64);
+        }
+        int rc = sv_verify_host(ctx, kind, msg.data(), key.data(), sig.data(), m, out.data());
+        if (rc) return rc;
+        for (size_t j = 0; j < m; j++) verdicts[idx[j]] = out[j];
+    }
+    ctx->queue.clear();
+    return SV_OK;
+}
+
+// ---- synthetic workload + probes ----------------------------------------------------------------
+extern "C" int sv_synth_device(sv_ctx* ctx, int kind, uint64_t seed, size_t n, void* d_msg32, void* d_key,
+                               void* d_sig64, void* stream) {
+    if (!ctx || sv_key_size(kind) == 0 || (n && (!d_msg32 || !d_key || !d_sig64))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    unsigned grid = (unsigned)((n + 127) / 128);
+    if (kind == SV_KIND_ECDSA33)
+        k_synth<SV_KIND_ECDSA33><<<grid, 128, 0, st>>>(seed, n, ctx->d_gtab, (u8*)d_msg32, (u8*)d_key, (u8*)d_sig64);
+    else if (kind == SV_KIND_ECDSA_XY)
+        k_synth<SV_KIND_ECDSA_XY><<<grid, 128, 0, st>>>(seed, n, ctx->d_gtab, (u8*)d_msg32, (u8*)d_key, (u8*)d_sig64);
+    else
+        k_synth<SV_KIND_SCHNORR><<<grid, 128, 0, st>>>(seed, n, ctx->d_gtab, (u8*)d_msg32, (u8*)d_key, (u8*)d_sig64);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return SV_OK;
+}
+
+extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 3) return SV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int iters = (mode >= 2) ? 2000 : 4000;
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        k_probe<<<blocks, threads, 0, ctx->stream>>>(mode, iters, ctx->d_sink);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+        ctx->launches += 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double per_thread = (mode == 0) ? (double)iters * 32.0 : (mode == 1) ? (double)iters * 32.0 : (double)iters * 2.0;
+    *ops_per_sec = per_thread * blocks * threads / (best * 1e-3);
+    return SV_OK;
+}
+extern "C" int sv_probe_imad_peak(sv_ctx* ctx, double* imad_per_sec) { return sv_probe(ctx, 0, imad_per_sec); }
+
+// pinned host memory for callers that want full-speed H2D/D2H
+extern "C" void* sv_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void sv_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}

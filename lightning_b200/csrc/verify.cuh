@@ -200,10 +200,12 @@ SV_HD bool key_decode(ge& Q, int kind, const u8* key) {
     }
 }
 
-SV_HD u32 window4(const u32 mag[5], int i) {  // bits [4i+1, 4i+5) of the 160-bit magnitude
+// bits [4i+1, 4i+5) of a 160-bit magnitude, i <= 31 (highest bit touched is 128, so the sign bit
+// kept in bit 159 never enters a window); read straight from the work record
+SV_HD u32 window4(const u32* mag, int i) {
     int off = 4 * i + 1;
     int l = off >> 5, sh = off & 31;
-    u64 two = ((u64)(l < 4 ? mag[l + 1] : 0u) << 32) | mag[l];
+    u64 two = ((u64)mag[l + 1] << 32) | mag[l];  // l <= 3
     return (u32)(two >> sh) & 15u;
 }
 
@@ -274,19 +276,17 @@ SV_HD void qtable_fetch(ge& p, const qtab_entry* tab, u32 v, u32 sneg, bool lam)
 }
 
 // R = u1*G + u2*Q in true Jacobian coordinates.
-SV_HD void ecmult_uniform(gej& R, const sv_work& w, const ge& Q, const ge_mem* gtab, qtab_entry* tab) {
+SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* gtab, qtab_entry* tab) {
     fe zc;
     qtable_build(tab, zc, Q);
-    u32 m1[5], m2[5];
-    SV_UNROLL
-    for (int i = 0; i < 5; i++) { m1[i] = w.k1[i]; m2[i] = w.k2[i]; }
-    u32 s1 = m1[4] >> 31, s2 = m2[4] >> 31;
-    m1[4] &= 0x7FFFFFFFu;
-    m2[4] &= 0x7FFFFFFFu;
+    const u32* m1 = w->k1;
+    const u32* m2 = w->k2;
+    u32 t1 = m1[4], t2 = m2[4];
+    u32 s1 = t1 >> 31, s2 = t2 >> 31;
     ge p;
     // top window (i = 32): digit = 2*(mag >> 129) + 1, always positive
     {
-        u32 v1 = (m1[4] >> 1) & 7u, v2 = (m2[4] >> 1) & 7u;
+        u32 v1 = (t1 >> 1) & 7u, v2 = (t2 >> 1) & 7u;
         qtable_fetch(p, tab, v1 + 8u, s1, false);
         gej_set_ge(R, p);
         qtable_fetch(p, tab, v2 + 8u, s2, true);
@@ -316,7 +316,7 @@ SV_HD void ecmult_uniform(gej& R, const sv_work& w, const ge& Q, const ge_mem* g
 #pragma unroll 1
 #endif
     for (int row = 0; row < 16; row++) {
-        int d = w.gd[row];
+        int d = w->gd[row];
         if (d != 0) {
             u32 a = (u32)(d < 0 ? -d : d);
             ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
@@ -360,14 +360,15 @@ SV_HD u32 schnorr_final(const gej& R, const u8* sig64) {
 }
 
 // whole curve side for one item
-SV_HD u32 verify_curve_side(int kind, const sv_work& w, const u8* key, const u8* sig64, const ge_mem* gtab,
+SV_HD u32 verify_curve_side(int kind, const sv_work* w, const u8* key, const u8* sig64, const ge_mem* gtab,
                             qtab_entry* tab) {
-    if (!(w.flags & SV_WF_VALID)) return 0;
+    u32 flags = w->flags;
+    if (!(flags & SV_WF_VALID)) return 0;
     ge Q;
     if (!key_decode(Q, kind, key)) return 0;
     gej R;
     ecmult_uniform(R, w, Q, gtab, tab);
-    return (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, w.flags);
+    return (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);
 }
 
 // =================================================================================================

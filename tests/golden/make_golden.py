@@ -1,0 +1,245 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures from the reference tree (run HERE, where /root/reference
+exists; the GPU box only sees the generated files).  Vectors are data, not code:
+
+  wycheproof_ecdsa.json   463 Wycheproof ECDSA secp256k1/SHA-256 "bitcoin" vectors
+                          (src/wycheproof/ecdsa_secp256k1_sha256_bitcoin_test.json; driver tests.c:7415-7442),
+                          DER signatures converted to the 64-byte compact form with the reference's own
+                          strict DER parser (vectors it refuses to parse keep sig64 = null, verdict 0)
+  bip340.json             BIP-340 vectors 0-14 as embedded in modules/schnorrsig/tests_impl.h:206-628
+  pubkey_parse.json       valid / invalid 33-byte encodings from tests.c run_ec_pubkey_parse_test (:5893-)
+  gossip_subset.bin/.json a slice of tests/data/routing_gossip_store (real mainnet channel_announcement,
+                          node_announcement, channel_update messages; all signatures valid under the reference)
+  chan_ann_3703.json      the mainnet channel_announcement of gossipd/test/run-check_channel_announcement.c
+  ecmult_kat.json         the two digests of tests.c:5657-5726 (SHA-256 over x*G for derived scalars)
+
+Every expected verdict written here is re-checked against oracle/_ref (the unmodified reference) at
+generation time.
+"""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import struct
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tests import util  # noqa: E402
+
+REF = "/root/reference"
+S = REF + "/external/libwally-core/src/secp256k1"
+OUT = os.path.dirname(os.path.abspath(__file__))
+ref = util.load_ref()
+P = util.P
+
+
+def arr(b):
+    return np.frombuffer(bytes(b), dtype=np.uint8).copy()
+
+
+def wycheproof():
+    j = json.load(open(S + "/src/wycheproof/ecdsa_secp256k1_sha256_bitcoin_test.json"))
+    out = []
+    for g in j["testGroups"]:
+        # "publicKey" (newer schema) or "key"
+        keyobj = g.get("publicKey") or g.get("key")
+        pk = bytes.fromhex(keyobj["uncompressed"])
+        p33 = np.zeros(33, np.uint8)
+        pxy = np.zeros(64, np.uint8)
+        assert ref.ref_pubkey_convert(P(arr(pk)), ctypes.c_size_t(len(pk)), P(p33), P(pxy))
+        for t in g["tests"]:
+            msg = bytes.fromhex(t["msg"])
+            h = hashlib.sha256(msg).digest()
+            der = bytes.fromhex(t["sig"])
+            s64 = np.zeros(64, np.uint8)
+            ok = ref.ref_sig_der_to_compact(P(arr(der if der else b'\x00')), ctypes.c_size_t(len(der)), P(s64))
+            exp = 1 if t["result"] == "valid" else 0
+            assert t["result"] in ("valid", "invalid")
+            if ok:
+                got = util.ref_verify(ref, 0, arr(h).reshape(1, 32), p33.reshape(1, 33), s64.reshape(1, 64))[0]
+            else:
+                got = 0
+            assert got == exp, (t["tcId"], got, exp)
+            out.append(dict(tcId=t["tcId"], comment=t.get("comment", ""), msg32=h.hex(), pub33=bytes(p33).hex(),
+                            pubxy=bytes(pxy).hex(), sig64=bytes(s64).hex() if ok else None, expected=exp))
+    assert len(out) == 463, len(out)
+    json.dump(out, open(OUT + "/wycheproof_ecdsa.json", "w"), indent=0)
+    print("wycheproof:", len(out), "vectors,", sum(1 for o in out if o["sig64"]), "DER-parseable,",
+          sum(o["expected"] for o in out), "valid")
+
+
+def c_array(block, name):
+    m = re.search(r"const unsigned char " + name + r"\[(?:32|64)?\]\s*=\s*\{([^}]*)\}", block)
+    if not m:
+        return None
+    return bytes(int(x, 16) for x in re.findall(r"0x([0-9A-Fa-f]{2})", m.group(1)))
+
+
+def bip340():
+    src = open(S + "/src/modules/schnorrsig/tests_impl.h").read()
+    start = src.index("static void test_schnorrsig_bip_vectors(void)")
+    body = src[start:]
+    blocks = re.split(r"/\* Test vector (\d+) \*/", body)
+    out = []
+    for i in range(1, len(blocks), 2):
+        num, blk = int(blocks[i]), blocks[i + 1]
+        if num > 14:
+            break  # 15-18 use messages that are not 32 bytes; CLN always signs 32-byte hashes (signature.c:428)
+        pk, msg, sig = c_array(blk, "pk"), c_array(blk, "msg"), c_array(blk, "sig")
+        m = re.search(r"check_verify\(pk, msg, sizeof\(msg\), sig, (\d)\)", blk)
+        if m:
+            exp = int(m.group(1))
+        else:
+            assert "CHECK(!secp256k1_xonly_pubkey_parse" in blk, num
+            exp, msg, sig = 0, bytes(32), bytes(64)
+        got = util.ref_verify(ref, 2, arr(msg).reshape(1, 32), arr(pk).reshape(1, 32), arr(sig).reshape(1, 64))[0]
+        assert got == exp, (num, got, exp)
+        out.append(dict(index=num, xonly=pk.hex(), msg32=msg.hex(), sig64=sig.hex(), expected=exp))
+    assert [o["index"] for o in out] == list(range(15))
+    json.dump(out, open(OUT + "/bip340.json", "w"), indent=0)
+    print("bip340:", len(out), "vectors,", sum(o["expected"] for o in out), "valid")
+
+
+def pubkey_parse():
+    src = open(S + "/src/tests.c").read()
+    start = src.index("static void run_ec_pubkey_parse_test(void)")
+    body = src[start:start + 40000]
+    out = []
+    for name, exp in (("valid", 1), ("invalid", 0)):
+        m = re.search(r"const unsigned char " + name + r"\[\w+\]\[64\]\s*=\s*\{(.*?)\n    \};", body, re.S)
+        rows = re.findall(r"\{([^{}]*)\}", m.group(1), re.S)
+        for r in rows:
+            xy = bytes(int(x, 16) for x in re.findall(r"0x([0-9A-Fa-f]{2})", r))
+            assert len(xy) == 64
+            # the reference test prepends 0x02/0x03 according to y parity for the compressed form
+            for pfx in (2, 3):
+                k = bytes([pfx]) + xy[:32]
+                o33 = np.zeros(33, np.uint8)
+                oxy = np.zeros(64, np.uint8)
+                got = ref.ref_pubkey_convert(P(arr(k)), ctypes.c_size_t(33), P(o33), P(oxy))
+                out.append(dict(pub33=k.hex(), expected=int(bool(got)), xy=bytes(oxy).hex() if got else None, table=name))
+            k65 = arr(b"\x04" + xy)
+            got65 = ref.ref_pubkey_convert(P(k65), ctypes.c_size_t(65), P(np.zeros(33, np.uint8)), P(np.zeros(64, np.uint8)))
+            assert bool(got65) == bool(exp), (name, xy.hex())
+            out.append(dict(pubxy=xy.hex(), expected=int(bool(got65)), table=name))
+    json.dump(out, open(OUT + "/pubkey_parse.json", "w"), indent=0)
+    print("pubkey_parse:", len(out), "encodings,", sum(o["expected"] for o in out), "valid")
+
+
+WIRE_CHANNEL_ANNOUNCEMENT, WIRE_NODE_ANNOUNCEMENT, WIRE_CHANNEL_UPDATE = 256, 257, 258
+
+
+def parse_gossip_store(path):
+    """common/gossip_store.h:15-51 — 1 version byte, then records: be16 flags, be16 len, be32 crc, be32 ts, msg."""
+    data = open(path, "rb").read()
+    pos, msgs = 1, []
+    while pos + 12 <= len(data):
+        flags, ln, crc, ts = struct.unpack(">HHII", data[pos:pos + 12])
+        msg = data[pos + 12:pos + 12 + ln]
+        pos += 12 + ln
+        if len(msg) >= 2:
+            msgs.append((struct.unpack(">H", msg[:2])[0], msg))
+    return msgs
+
+
+def gossip_items(msgs):
+    """Expand gossip messages into signature items exactly as gossipd/sigcheck.c does:
+    channel_announcement: hash msg[258:], sigs at 2,66,130,194 by node_id_1, node_id_2, bitcoin_key_1, bitcoin_key_2
+    node_announcement:    hash msg[66:],  sig at 2, key = node_id (after flen+features and timestamp)
+    channel_update:       hash msg[66:],  sig at 2, key = node_id_{1|2} of the channel by channel_flags & 1"""
+    chans = {}
+    items = []  # (msg_index, hash_off, sig_off, key33)
+    for mi, (typ, m) in enumerate(msgs):
+        if typ == WIRE_CHANNEL_ANNOUNCEMENT:
+            flen = struct.unpack(">H", m[258:260])[0]
+            p = 260 + flen + 32
+            scid = m[p:p + 8]
+            p += 8
+            keys = [m[p + 33 * k:p + 33 * k + 33] for k in range(4)]
+            chans[scid] = (keys[0], keys[1])
+            for k in range(4):
+                items.append((mi, 258, 2 + 64 * k, keys[k]))
+        elif typ == WIRE_NODE_ANNOUNCEMENT:
+            flen = struct.unpack(">H", m[66:68])[0]
+            p = 68 + flen + 4
+            items.append((mi, 66, 2, m[p:p + 33]))
+        elif typ == WIRE_CHANNEL_UPDATE:
+            scid = m[2 + 64 + 32:2 + 64 + 32 + 8]
+            chflags = m[2 + 64 + 32 + 8 + 4 + 1]
+            if scid in chans:
+                items.append((mi, 66, 2, chans[scid][chflags & 1]))
+    return items
+
+
+def gossip():
+    msgs = parse_gossip_store(REF + "/tests/data/routing_gossip_store")
+    counts = {}
+    for t, _ in msgs:
+        counts[t] = counts.get(t, 0) + 1
+    print("gossip_store message types:", counts)
+    # subset: first 1500 channel_announcements, the updates that reference them, first 400 node_announcements
+    keep, nca, nna, ncu, scids = [], 0, 0, 0, set()
+    for typ, m in msgs:
+        if typ == WIRE_CHANNEL_ANNOUNCEMENT and nca < 1500:
+            flen = struct.unpack(">H", m[258:260])[0]
+            scids.add(m[260 + flen + 32:260 + flen + 40])
+            keep.append((typ, m)); nca += 1
+        elif typ == WIRE_NODE_ANNOUNCEMENT and nna < 400:
+            keep.append((typ, m)); nna += 1
+        elif typ == WIRE_CHANNEL_UPDATE and ncu < 1200 and m[98:106] in scids:
+            keep.append((typ, m)); ncu += 1
+    items = gossip_items(keep)
+    # verify everything with the reference (sha256d + parse + verify)
+    n = len(items)
+    msg32 = np.zeros((n, 32), np.uint8); key = np.zeros((n, 33), np.uint8); sig = np.zeros((n, 64), np.uint8)
+    for i, (mi, hoff, soff, k) in enumerate(items):
+        m = keep[mi][1]
+        tail = arr(m[hoff:])
+        ref.ref_sha256d(P(tail), ctypes.c_size_t(tail.size), P(msg32[i]))
+        key[i] = arr(k); sig[i] = arr(m[soff:soff + 64])
+    v = util.ref_verify(ref, 0, msg32, key, sig)
+    assert v.all(), f"{n - v.sum()} fixture signatures fail under the reference"
+    blob = b"".join(struct.pack(">H", len(m)) + m for _, m in keep)
+    open(OUT + "/gossip_subset.bin", "wb").write(blob)
+    json.dump(dict(source="tests/data/routing_gossip_store (reference v26.04.1)", format="repeat: be16 len, wire message",
+                   channel_announcements=nca, node_announcements=nna, channel_updates=ncu, signatures=n,
+                   all_valid_under_reference=True, full_store_counts={str(k): v for k, v in counts.items()}),
+              open(OUT + "/gossip_subset.json", "w"), indent=1)
+    print("gossip subset:", nca, "CA,", nna, "NA,", ncu, "CU ->", n, "signatures, all valid;", len(blob), "bytes")
+
+
+def chan_ann_3703():
+    src = open(REF + "/gossipd/test/run-check_channel_announcement.c").read()
+    m = re.search(r'tal_hexdata\(\w+,\s*"([0-9a-f]+)"', src)
+    if not m:
+        hexes = re.findall(r'"([0-9a-f]{64,})"', src)
+        h = "".join(hexes)
+    else:
+        h = m.group(1)
+    json.dump(dict(source="gossipd/test/run-check_channel_announcement.c (issue #3703, scid 628813x1594x1)", msg=h),
+              open(OUT + "/chan_ann_3703.json", "w"), indent=1)
+    print("chan_ann_3703:", len(h) // 2, "bytes")
+
+
+def ecmult_kat():
+    src = open(S + "/src/tests.c").read()
+    def digest(name):
+        m = re.search(r"static const unsigned char " + name + r"\[32\] = \{(.*?)\};", src, re.S)
+        return bytes(int(x, 16) for x in re.findall(r"0x([0-9a-f]{2})", m.group(1))).hex()
+    out = [dict(prefix=4808378, iters=1024, sha256=digest("expected32_6bit20")),
+           dict(prefix=1607366309, iters=2048, sha256=digest("expected32_8bit8"))]
+    json.dump(out, open(OUT + "/ecmult_kat.json", "w"), indent=1)
+    print("ecmult_kat:", out)
+
+
+if __name__ == "__main__":
+    wycheproof()
+    bip340()
+    pubkey_parse()
+    gossip()
+    chan_ann_3703()
+    ecmult_kat()

@@ -165,6 +165,6 @@ void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, si
     }
     qtab_entry tab[8];
     for (size_t i = 0; i < n; i++)
-        out[i] = (u8)verify_curve_side(kind, work[i], key + keylen * i, sig + 64 * i, g_table.data(), tab);
+        out[i] = (u8)verify_curve_side(kind, &work[i], key + keylen * i, sig + 64 * i, g_table.data(), tab);
 }
 }

@@ -1,0 +1,108 @@
+"""Shared test helpers: oracle loaders and seeded workload generation (tests only)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+P_FIELD = 2**256 - 2**32 - 977
+_p8 = ctypes.POINTER(ctypes.c_uint8)
+
+
+def P(a):
+    return a.ctypes.data_as(_p8)
+
+
+def load_ref():
+    path = os.path.join(ROOT, "oracle", "_ref", "libsecp_ref.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        else:
+            raise RuntimeError("oracle/_ref/libsecp_ref.so missing and /root/reference absent")
+    return ctypes.CDLL(path)
+
+
+def load_port():
+    path = os.path.join(ROOT, "oracle", "libsecp_port.so")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    return ctypes.CDLL(path)
+
+
+def load_emul():
+    from lightning_b200 import build
+    return ctypes.CDLL(build.build_host_emul())
+
+
+def ref_verify(ref, kind, msg, key, sig, threads=1):
+    n = msg.shape[0]
+    out = np.zeros(n, np.uint8)
+    fn = [ref.ref_ecdsa_verify_batch, ref.ref_ecdsa_verify_batch_xy, ref.ref_schnorr_verify_batch][kind]
+    fn(P(msg), P(key), P(sig), ctypes.c_size_t(n), P(out), threads)
+    return out
+
+
+def make_signed(ref, n, seed):
+    """n seeded random keys/messages signed by the reference: returns dict of arrays."""
+    rng = np.random.default_rng(seed)
+    sk = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    msg = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    pub33 = np.zeros((n, 33), np.uint8)
+    pubxy = np.zeros((n, 64), np.uint8)
+    sig = np.zeros((n, 64), np.uint8)
+    xonly = np.zeros((n, 32), np.uint8)
+    ssig = np.zeros((n, 64), np.uint8)
+    for i in range(n):
+        assert ref.ref_pubkey_create(P(sk[i]), P(pub33[i]), P(pubxy[i]))
+        assert ref.ref_ecdsa_sign(P(sk[i]), P(msg[i]), P(sig[i]))
+        assert ref.ref_schnorr_sign(P(sk[i]), P(msg[i]), P(ssig[i]), P(xonly[i]))
+    return dict(msg=msg, pub33=pub33, pubxy=pubxy, sig=sig, xonly=xonly, ssig=ssig)
+
+
+def corrupt(w, every=10):
+    """SURVEY.md §8(d) corruption classes, round-robin on every `every`-th item (in place, returns w)."""
+    n = w["msg"].shape[0]
+    for cls, i in enumerate(range(0, n, every)):
+        c = cls % 11
+        j = (i + 1) % n
+        if c == 0:
+            w["msg"][i, 5] ^= 4
+        elif c == 1:
+            w["sig"][i, 7] ^= 1
+            w["ssig"][i, 7] ^= 1
+        elif c == 2:
+            w["sig"][i, 40] ^= 1
+            w["ssig"][i, 40] ^= 1
+        elif c == 3:  # high S
+            s = int.from_bytes(bytes(w["sig"][i, 32:]), "big")
+            w["sig"][i, 32:] = np.frombuffer((N_ORDER - s).to_bytes(32, "big"), dtype=np.uint8)
+            w["ssig"][i, 32:] = 255  # s >= n
+        elif c == 4:  # someone else's key
+            w["pub33"][i] = w["pub33"][j]
+            w["pubxy"][i] = w["pubxy"][j]
+            w["xonly"][i] = w["xonly"][j]
+        elif c == 5:  # bad prefix / y off curve
+            w["pub33"][i, 0] = 4
+            w["pubxy"][i, 63] ^= 1
+            w["xonly"][i, 31] ^= 1
+        elif c == 6:  # x >= p
+            w["pub33"][i, 1:] = 255
+            w["pubxy"][i, :32] = 255
+            w["xonly"][i, :] = 255
+        elif c == 7:  # flip a key bit (usually lands on a non-residue or a different point)
+            w["pub33"][i, 20] ^= 1
+            w["pubxy"][i, 20] ^= 1
+            w["xonly"][i, 20] ^= 1
+        elif c == 8:  # wrong parity / negated R
+            w["pub33"][i, 0] ^= 1
+            w["ssig"][i, :32] = np.frombuffer(
+                ((P_FIELD - int.from_bytes(bytes(w["ssig"][i, :32]), "big")) % P_FIELD).to_bytes(32, "big"), np.uint8)
+        elif c == 9:  # r = 0 / r >= p
+            w["sig"][i, :32] = 0
+            w["ssig"][i, :32] = 255
+        elif c == 10:  # s = 0 / r >= n
+            w["sig"][i, 32:] = 0
+            w["sig"][j % n, :32] = 255
+    return w
