@@ -86,6 +86,8 @@ int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_l
 int sv_verify_device(sv_ctx *ctx, int kind, const void *d_msg32, const void *d_key, const void *d_sig64, size_t n,
                      void *d_verdicts, void *d_bitmap, void *stream);
 int sv_sync(sv_ctx *ctx, void *stream);
+/* the context's own cudaStream_t (as void*), e.g. to record timing events on it */
+void *sv_get_stream(const sv_ctx *ctx);
 
 /* ---- deferral queue: enqueue returns the item's index in the pending batch; sv_flush verifies all
  *      pending items of every kind and writes one verdict byte per item in enqueue order. ---- */
@@ -119,10 +121,22 @@ typedef struct {
 } sv_info;
 int sv_get_info(const sv_ctx *ctx, sv_info *info);
 
+/* per-kernel device timing: when enabled, every sv_verify_* call records CUDA events on its launch stream
+ * around the scalar-side and curve-side kernels; read them back after synchronising. */
+int sv_set_profiling(sv_ctx *ctx, int on);
+int sv_get_last_timing(sv_ctx *ctx, float *prep_ms, float *main_ms);
+
 /* integer-pipe roofline probe: runs a dependent-chain IMAD.WIDE.U32 microbenchmark and returns the
  * achieved 32x32->64 multiply-accumulates per second on this device (the roofline denominator
  * SURVEY.md §8d asks to be measured, not assumed). */
 int sv_probe_imad_peak(sv_ctx *ctx, double *imad_per_sec);
+/* individual probes (see engine.cu k_probe_*): 0 IMAD.WIDE peak, 1 4-deep carry chains, 2 fe_mul/s, 3 fe_sqr/s,
+ * 4 8-deep carry chains, 5 carry-save, 6 32-bit IMAD lo/hi, 7 IADD3 carry chains */
+int sv_probe(sv_ctx *ctx, int mode, double *ops_per_sec);
+
+/* pinned host memory (cudaHostAlloc) for callers that want full-speed copies */
+void *sv_host_alloc(size_t bytes);
+void sv_host_free(void *p);
 
 #ifdef __cplusplus
 }

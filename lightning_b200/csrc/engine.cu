@@ -217,60 +217,170 @@ __global__ void __launch_bounds__(128) k_synth(u64 seed, size_t n, const ge_mem*
 }
 
 // ---- integer-pipe probes ------------------------------------------------------------------------
-// mode 0: independent IMAD.WIDE.U32 accumulations (8 chains/thread)   -> multiply-accumulates/s
-// mode 1: carry-chained IMAD.WIDE.U32.X rows exactly as u256_mul_wide issues them
-// mode 2: fe_mul throughput (field multiplications/s)   mode 3: fe_sqr throughput
-__global__ void __launch_bounds__(256) k_probe(int mode, int iters, u32* sink) {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mode == 0) {
-        u64 a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-        u32 x = t * 2654435761u + 12345u, y = t ^ 0x9E3779B9u;
+// Each probe is its own kernel so that ncu reports them separately.  All run 256 threads x 8 CTAs/SM.
+//   0 k_probe_imad_wide   independent IMAD.WIDE.U32 accumulations (no carries)      -> MAC/s (roofline peak)
+//   1 k_probe_cmad4       4-deep IMAD.WIDE.U32(.X) carry chains as u256_mul_wide issues them -> MAC/s
+//   2 k_probe_fe_mul      field multiplications/s          3 k_probe_fe_sqr   field squarings/s
+//   4 k_probe_chain8      8-deep IMAD.WIDE.U32.X chains    -> MAC/s
+//   5 k_probe_carry_save  IMAD.WIDE.U32 with carry-OUT only + one IADD3.X per product -> MAC/s
+//   6 k_probe_imad32      separate 32-bit IMAD (lo) / IMAD.HI  -> instr/s
+//   7 k_probe_addc        8-long IADD3(.X) carry chains -> adds/s
+#define PROBE_PROLOGUE u32 t = blockIdx.x * blockDim.x + threadIdx.x
+__global__ void __launch_bounds__(256) k_probe_imad_wide(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    u32 lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo[k] = t * 2654435761u + k; hi[k] = t ^ (k * 0x9E3779B9u); }
+    u32 y = t | 3u;
 #pragma unroll 1
-        for (int i = 0; i < iters; i++) {
+    for (int i = 0; i < iters; i++) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\t"
-                             "mad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
-                             "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
-                             "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-                             : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7)
-                             : "r"(x), "r"(y));
-            }
+        for (int r = 0; r < 4; r++) {
+            // acc_k += lo(acc_{k+1}) * y : eight independent 64-bit multiply-accumulates per step whose
+            // multiplicands change every step (so ptxas cannot strength-reduce them to additions)
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                             : "+r"(lo[k]), "+r"(hi[k])
+                             : "r"(lo[(k + 1) & 7]), "r"(y));
         }
-        u64 s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
-        if (s == 0x1234567ull) sink[0] = (u32)s;
-    } else if (mode == 1) {
-        u32 E[8], O[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { E[k] = t + k; O[k] = t * 3 + k; }
-        u32 a0 = t | 1, a1 = t ^ 0xABCDEFu, a2 = t * 7 + 1, a3 = ~t, b = t * 2654435761u;
-        u32 cs = 0;
-#pragma unroll 1
-        for (int i = 0; i < iters; i++) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                cs += sv_cmad4(E, a0, a1, a2, a3, b);
-                cs += sv_cmad4(O, a1, a2, a3, a0, b);
-            }
-        }
-        u32 s = cs;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s ^= E[k] ^ O[k];
-        if (s == 0x12345u) sink[0] = s;
-    } else {
-        fe a, b;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { a.v[k] = t * 2654435761u + k; b.v[k] = (t ^ 0x5bd1e995u) * (k + 3); }
-#pragma unroll 1
-        for (int i = 0; i < iters; i++) {
-            if (mode == 2) { fe_mul(a, a, b); fe_mul(b, b, a); }
-            else { fe_sqr(a, a); fe_sqr(b, b); }
-        }
-        u32 s = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s ^= a.v[k] ^ b.v[k];
-        if (s == 0x12345u) sink[0] = s;
     }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= lo[k] ^ hi[k];
+    if (s == 0x1234567u) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_cmad4(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    u32 E[8], O[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { E[k] = t + k; O[k] = t * 3 + k; }
+    u32 a0 = t | 1, a1 = t ^ 0xABCDEFu, a2 = t * 7 + 1, a3 = ~t, b = t * 2654435761u;
+    u32 cs = 0;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            cs += sv_cmad4(E, a0, a1, a2, a3, b);
+            cs += sv_cmad4(O, a1, a2, a3, a0, b);
+        }
+    }
+    u32 s = cs;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= E[k] ^ O[k];
+    if (s == 0x12345u) sink[0] = s;
+}
+template <int SQR>
+__global__ void __launch_bounds__(256) k_probe_fe(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    fe a, b;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a.v[k] = t * 2654435761u + k; b.v[k] = (t ^ 0x5bd1e995u) * (k + 3); }
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        if (!SQR) { fe_mul(a, a, b); fe_mul(b, b, a); }
+        else { fe_sqr(a, a); fe_sqr(b, b); }
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a.v[k] ^ b.v[k];
+    if (s == 0x12345u) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_chain8(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    u32 A[16], B[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { A[k] = t + k; B[k] = t * 5 + k; }
+    u32 x0 = t | 1, x1 = t ^ 0xABCDEFu, x2 = t * 7 + 1, x3 = ~t, y = t * 2654435761u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+#define CHAIN8(ACC)                                                                                              \
+    asm volatile("mad.lo.cc.u32 %0, %16, %20, %0;\n\tmadc.hi.cc.u32 %1, %16, %20, %1;\n\t"                         \
+                 "madc.lo.cc.u32 %2, %17, %20, %2;\n\tmadc.hi.cc.u32 %3, %17, %20, %3;\n\t"                        \
+                 "madc.lo.cc.u32 %4, %18, %20, %4;\n\tmadc.hi.cc.u32 %5, %18, %20, %5;\n\t"                        \
+                 "madc.lo.cc.u32 %6, %19, %20, %6;\n\tmadc.hi.cc.u32 %7, %19, %20, %7;\n\t"                        \
+                 "madc.lo.cc.u32 %8, %17, %20, %8;\n\tmadc.hi.cc.u32 %9, %17, %20, %9;\n\t"                        \
+                 "madc.lo.cc.u32 %10, %18, %20, %10;\n\tmadc.hi.cc.u32 %11, %18, %20, %11;\n\t"                    \
+                 "madc.lo.cc.u32 %12, %19, %20, %12;\n\tmadc.hi.cc.u32 %13, %19, %20, %13;\n\t"                    \
+                 "madc.lo.cc.u32 %14, %16, %20, %14;\n\tmadc.hi.u32 %15, %16, %20, %15;"                           \
+                 : "+r"(ACC[0]), "+r"(ACC[1]), "+r"(ACC[2]), "+r"(ACC[3]), "+r"(ACC[4]), "+r"(ACC[5]), "+r"(ACC[6]), \
+                   "+r"(ACC[7]), "+r"(ACC[8]), "+r"(ACC[9]), "+r"(ACC[10]), "+r"(ACC[11]), "+r"(ACC[12]),           \
+                   "+r"(ACC[13]), "+r"(ACC[14]), "+r"(ACC[15])                                                      \
+                 : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y))
+            CHAIN8(A);
+            CHAIN8(B);
+        }
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s ^= A[k] ^ B[k];
+    if (s == 0x12345u) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_carry_save(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    u32 lo[8], hi[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo[k] = t + k; hi[k] = t * 3 + k; c[k] = k; }
+    u32 x = t * 2654435761u + 12345u, y = t ^ 0x9E3779B9u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                             : "+r"(lo[k]), "+r"(hi[k]), "+r"(c[k])
+                             : "r"(x), "r"(y));
+        }
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= lo[k] ^ hi[k] ^ c[k];
+    if (s == 0x12345u) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_imad32(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    u32 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = t + k;
+    u32 x = t * 2654435761u + 12345u, y = t ^ 0x9E3779B9u, z = t * 31 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k += 2)
+                asm volatile("mad.lo.u32 %0, %2, %3, %0;\n\tmad.hi.u32 %1, %2, %4, %1;"
+                             : "+r"(a[k]), "+r"(a[k + 1])
+                             : "r"(x), "r"(y), "r"(z));
+        }
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    if (s == 0x12345u) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_addc(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    u32 a[8], b[8], c[8], d[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = t + k; b[k] = t * 3 + k; c[k] = t ^ k; d[k] = ~t + k; }
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            u256_add(a, a, b);
+            u256_add(c, c, d);
+            u256_add(b, b, c);
+            u256_add(d, d, a);
+        }
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k] ^ b[k] ^ c[k] ^ d[k];
+    if (s == 0x12345u) sink[0] = s;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -304,6 +414,8 @@ struct sv_ctx {
     u32* d_len;
     size_t span_cap;
     u32* d_sink;
+    int profiling;
+    cudaEvent_t ev[3];  // before prep, between prep and main, after main (profiling mode only)
     unsigned long long launches;
     std::vector<sv_queue_item> queue;
     std::string err;
@@ -365,6 +477,8 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     ctx->d_msg = ctx->d_key = ctx->d_sig = ctx->d_verdict = ctx->d_data = nullptr;
     ctx->d_work = nullptr; ctx->d_off = nullptr; ctx->d_len = nullptr;
     ctx->launches = 0;
+    ctx->profiling = 0;
+    ctx->ev[0] = ctx->ev[1] = ctx->ev[2] = nullptr;
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { int rc = fail(nullptr, SV_ERR_CUDA, "cudaGetDeviceProperties", e); delete ctx; return rc; }
@@ -400,6 +514,7 @@ extern "C" void sv_destroy(sv_ctx* ctx) {
     cudaFree(ctx->d_gtab); cudaFree(ctx->d_bases); cudaFree(ctx->d_scratch); cudaFree(ctx->d_sink);
     cudaFree(ctx->d_msg); cudaFree(ctx->d_key); cudaFree(ctx->d_sig); cudaFree(ctx->d_verdict);
     cudaFree(ctx->d_work); cudaFree(ctx->d_data); cudaFree(ctx->d_off); cudaFree(ctx->d_len);
+    for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -425,12 +540,14 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
     if (n == 0) return SV_OK;
     int rc = ensure_work(ctx, n);
     if (rc) return rc;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
     if (kind == SV_KIND_SCHNORR) {
         k_prep_schnorr<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_work);
     } else {
         size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
         k_prep_ecdsa<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_msg, d_sig, n, ctx->d_work);
     }
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
     if (kind == SV_KIND_ECDSA33)
@@ -439,6 +556,7 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
         k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
     else
         k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
     ctx->launches += 2;
     if (d_bitmap) {
         size_t nb = (n + 255) / 256;
@@ -457,6 +575,24 @@ extern "C" int sv_verify_device(sv_ctx* ctx, int kind, const void* d_msg32, cons
     return launch_verify(ctx, kind, (const u8*)d_msg32, (const u8*)d_key, (const u8*)d_sig64, n, (u8*)d_verdicts,
                          (u32*)d_bitmap, st);
 }
+
+extern "C" int sv_set_profiling(sv_ctx* ctx, int on) {
+    if (!ctx) return SV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0])
+        for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ctx->ev[i]));
+    ctx->profiling = on ? 1 : 0;
+    return SV_OK;
+}
+// device time of the last sv_verify_* launch pair (call after the stream has been synchronised)
+extern "C" int sv_get_last_timing(sv_ctx* ctx, float* prep_ms, float* main_ms) {
+    if (!ctx || !ctx->profiling || !prep_ms || !main_ms) return SV_ERR_ARG;
+    CK(cudaEventElapsedTime(prep_ms, ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(main_ms, ctx->ev[1], ctx->ev[2]));
+    return SV_OK;
+}
+
+extern "C" void* sv_get_stream(const sv_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 extern "C" int sv_sync(sv_ctx* ctx, void* stream) {
     if (!ctx) return SV_ERR_ARG;
@@ -628,9 +764,9 @@ extern "C" int sv_synth_device(sv_ctx* ctx, int kind, uint64_t seed, size_t n, v
 }
 
 extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
-    if (!ctx || !ops_per_sec || mode < 0 || mode > 3) return SV_ERR_ARG;
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 7) return SV_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    const int iters = (mode >= 2) ? 2000 : 4000;
+    const int iters = (mode == 2 || mode == 3) ? 2000 : 4000;
     const int blocks = ctx->sm_count * 8, threads = 256;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -638,7 +774,16 @@ extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
         CK(cudaEventRecord(e0, ctx->stream));
-        k_probe<<<blocks, threads, 0, ctx->stream>>>(mode, iters, ctx->d_sink);
+        switch (mode) {
+            case 0: k_probe_imad_wide<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 1: k_probe_cmad4<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 2: k_probe_fe<0><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 3: k_probe_fe<1><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 4: k_probe_chain8<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 5: k_probe_carry_save<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 6: k_probe_imad32<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            default: k_probe_addc<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+        }
         CK(cudaEventRecord(e1, ctx->stream));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -648,8 +793,9 @@ extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    double per_thread = (mode == 0) ? (double)iters * 32.0 : (mode == 1) ? (double)iters * 32.0 : (double)iters * 2.0;
-    *ops_per_sec = per_thread * blocks * threads / (best * 1e-3);
+    // operations per thread per launch
+    static const double per_iter[8] = {32.0, 32.0, 2.0, 2.0, 32.0, 32.0, 32.0, 64.0};
+    *ops_per_sec = per_iter[mode] * iters * (double)blocks * threads / (best * 1e-3);
     return SV_OK;
 }
 extern "C" int sv_probe_imad_peak(sv_ctx* ctx, double* imad_per_sec) { return sv_probe(ctx, 0, imad_per_sec); }

@@ -259,18 +259,42 @@ SV_HD void fe_reduce512(fe& r, const u32 t[16]) {
 #endif
 }
 
-// reference: secp256k1_fe_mul (field_5x52_int128_impl.h:18)
+// reference: secp256k1_fe_mul (field_5x52_int128_impl.h:18), secp256k1_fe_sqr (:154)
+//
+// On the device these two are REAL FUNCTIONS (operands and result by value: the sm_100a ABI keeps all
+// 24 words in registers, no stack traffic).  ncu on the fully-inlined kernel showed the warps starved
+// for instructions (stall_no_instruction 4.5 per issue, issue slots 39 % busy): the ladder body was
+// ~44 KB of straight-line code against a 32 KB L1.5 / ~6 KB L0 instruction cache.  As functions the two
+// bodies (~4 KB together) stay L0-resident and carry ~85 % of all executed instructions.
+#if SV_DEVICE_CODE
+static __device__ __noinline__ fe fe_mul_fn(fe a, fe b) {
+    u32 t[16];
+    fe r;
+    u256_mul_wide(t, a.v, b.v);
+    fe_reduce512(r, t);
+    return r;
+}
+static __device__ __noinline__ fe fe_sqr_fn(fe a) {
+    u32 t[16];
+    fe r;
+    u256_sqr_wide(t, a.v);
+    fe_reduce512(r, t);
+    return r;
+}
+SV_HD void fe_mul(fe& r, const fe& a, const fe& b) { r = fe_mul_fn(a, b); }
+SV_HD void fe_sqr(fe& r, const fe& a) { r = fe_sqr_fn(a); }
+#else
 SV_HD void fe_mul(fe& r, const fe& a, const fe& b) {
     u32 t[16];
     u256_mul_wide(t, a.v, b.v);
     fe_reduce512(r, t);
 }
-// reference: secp256k1_fe_sqr (field_5x52_int128_impl.h:154)
 SV_HD void fe_sqr(fe& r, const fe& a) {
     u32 t[16];
     u256_sqr_wide(t, a.v);
     fe_reduce512(r, t);
 }
+#endif
 
 // r = a * k for a small constant k (k <= 2^16)   (reference: secp256k1_fe_mul_int)
 SV_HD void fe_mul_small(fe& r, const fe& a, u32 k) {

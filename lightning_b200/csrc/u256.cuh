@@ -127,7 +127,9 @@ SV_D void sv_merge16(u32 r[16], const u32 e[16], const u32 o[16]) {
 }
 #endif
 
-SV_HD void u256_mul_wide(u32 r[16], const u32 a[8], const u32 b[8]) {
+// Schoolbook 8x8 (64 IMAD.WIDE).  Kept as the reference implementation of the product and used by
+// the scalar-field code; the field code uses the Karatsuba / dedicated-square versions below.
+SV_HD void u256_mul_wide_schoolbook(u32 r[16], const u32 a[8], const u32 b[8]) {
 #if SV_DEVICE_CODE
     // E holds products whose low limb sits at an even position, O those at an odd position
     // (O[k] is limb position k+1).  Zero-initialised; ptxas folds the zeros into RZ operands.
@@ -159,7 +161,287 @@ SV_HD void u256_mul_wide(u32 r[16], const u32 a[8], const u32 b[8]) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// 128x128 -> 256 product (16 IMAD.WIDE), building block of the Karatsuba multiply
+// ---------------------------------------------------------------------------------------------
+#if SV_DEVICE_CODE
+SV_D u32 sv_cmad2(u32* acc, u32 a0, u32 a1, u32 b) {  // acc[0..3] += {a0,a1}*b ; returns carry-out
+    u32 c;
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c)
+        : "r"(a0), "r"(a1), "r"(b));
+    return c;
+}
+#endif
+SV_HD void u128_mul_wide(u32 r[8], const u32 a[4], const u32 b[4]) {
+#if SV_DEVICE_CODE
+    u32 E[10], O[10];
+    SV_UNROLL
+    for (int i = 0; i < 10; i++) { E[i] = 0; O[i] = 0; }
+    SV_UNROLL
+    for (int i = 0; i < 4; i++) {
+        u32* A = (i & 1) ? (O + i - 1) : (E + i);
+        u32* B = (i & 1) ? (E + i + 1) : (O + i);
+        u32 c = sv_cmad2(A, a[0], a[2], b[i]);
+        A[4] = c;
+        (void)sv_cmad2(B, a[1], a[3], b[i]);
+    }
+    r[0] = E[0];
+    asm("add.cc.u32 %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+#else
+    u64 t[8];
+    for (int i = 0; i < 8; i++) t[i] = 0;
+    for (int i = 0; i < 4; i++) {
+        u64 c = 0;
+        for (int j = 0; j < 4; j++) {
+            u64 p = (u64)a[j] * b[i] + t[i + j] + c;
+            t[i + j] = (u32)p;
+            c = p >> 32;
+        }
+        t[i + 4] = c;
+    }
+    for (int i = 0; i < 8; i++) r[i] = (u32)t[i];
+#endif
+}
+
+// |a - b| for 128-bit operands; returns 1 if a < b (i.e. the result was negated)
+SV_HD u32 u128_absdiff(u32 r[4], const u32 a[4], const u32 b[4]) {
+#if SV_DEVICE_CODE
+    u32 bw;
+    asm("sub.cc.u32 %0, %5, %9;\n\t"
+        "subc.cc.u32 %1, %6, %10;\n\t"
+        "subc.cc.u32 %2, %7, %11;\n\t"
+        "subc.cc.u32 %3, %8, %12;\n\t"
+        "subc.u32 %4, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    // bw = 0 or 0xFFFFFFFF ; conditional negate: (x ^ bw) - bw
+    u32 one = bw & 1u;
+    asm("add.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, 0;\n\t"
+        "addc.cc.u32 %2, %6, 0;\n\t"
+        "addc.u32 %3, %7, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+        : "r"(r[0] ^ bw), "r"(r[1] ^ bw), "r"(r[2] ^ bw), "r"(r[3] ^ bw), "r"(one));
+    return one;
+#else
+    u64 bw = 0;
+    u32 t[4];
+    for (int i = 0; i < 4; i++) {
+        u64 d = (u64)a[i] - b[i] - bw;
+        t[i] = (u32)d;
+        bw = (d >> 32) & 1;
+    }
+    u32 mask = bw ? 0xFFFFFFFFu : 0u;
+    u64 c = bw;
+    for (int i = 0; i < 4; i++) {
+        c += (u64)(t[i] ^ mask);
+        r[i] = (u32)c;
+        c >>= 32;
+    }
+    return (u32)bw;
+#endif
+}
+
+// Karatsuba, one level, subtractive form:
+//   a = a0 + a1 W, b = b0 + b1 W (W = 2^128):  ab = z0 + (z0 + z2 + s |a0-a1| |b1-b0|) W + z2 W^2
+// 48 IMAD.WIDE instead of 64.  On B200 the 64-bit IMAD.WIDE issues at half the rate of IADD3 (measured,
+// see profiles/), so trading 16 multiplies for ~60 carry-chain adds shortens the critical pipe.
+SV_HD void u256_mul_wide_karatsuba(u32 r[16], const u32 a[8], const u32 b[8]) {
+    u32 z0[8], z2[8], m[8], da[4], db[4];
+    u128_mul_wide(z0, a, b);
+    u128_mul_wide(z2, a + 4, b + 4);
+    u32 sa = u128_absdiff(da, a, a + 4);      // a0 - a1
+    u32 sb = u128_absdiff(db, b + 4, b);      // b1 - b0
+    u128_mul_wide(m, da, db);
+    u32 neg = sa ^ sb;                        // middle term is z0 + z2 - m when the signs differ
+#if SV_DEVICE_CODE
+    u32 mask = 0u - neg;
+    u32 t[9], z1[9];
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8])
+        : "r"(z0[0]), "r"(z0[1]), "r"(z0[2]), "r"(z0[3]), "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]),
+          "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
+    // z1 = t + (m ^ mask) + neg, ninth limb absorbs the two's-complement wrap (+mask)
+    asm("add.cc.u32 %0, %18, 0xFFFFFFFF;\n\t"   // carry := neg
+        "addc.cc.u32 %0, %9, %19;\n\t"
+        "addc.cc.u32 %1, %10, %20;\n\t"
+        "addc.cc.u32 %2, %11, %21;\n\t"
+        "addc.cc.u32 %3, %12, %22;\n\t"
+        "addc.cc.u32 %4, %13, %23;\n\t"
+        "addc.cc.u32 %5, %14, %24;\n\t"
+        "addc.cc.u32 %6, %15, %25;\n\t"
+        "addc.cc.u32 %7, %16, %26;\n\t"
+        "addc.u32 %8, %17, %27;"
+        : "=&r"(z1[0]), "=&r"(z1[1]), "=&r"(z1[2]), "=&r"(z1[3]), "=&r"(z1[4]), "=&r"(z1[5]), "=&r"(z1[6]), "=&r"(z1[7]),
+          "=&r"(z1[8])
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]),
+          "r"(neg), "r"(m[0] ^ mask), "r"(m[1] ^ mask), "r"(m[2] ^ mask), "r"(m[3] ^ mask), "r"(m[4] ^ mask),
+          "r"(m[5] ^ mask), "r"(m[6] ^ mask), "r"(m[7] ^ mask), "r"(mask));
+    // r = z0 + z1 W + z2 W^2
+    r[0] = z0[0]; r[1] = z0[1]; r[2] = z0[2]; r[3] = z0[3];
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, 0;\n\t"
+        "addc.cc.u32 %10, %22, 0;\n\t"
+        "addc.u32 %11, %23, 0;"
+        : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]),
+          "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]),
+          "r"(z1[0]), "r"(z1[1]), "r"(z1[2]), "r"(z1[3]), "r"(z1[4]), "r"(z1[5]), "r"(z1[6]), "r"(z1[7]), "r"(z1[8]));
+#else
+    u32 mask = neg ? 0xFFFFFFFFu : 0u;
+    u32 t[9], z1[9];
+    u64 c = 0;
+    for (int i = 0; i < 8; i++) { c += (u64)z0[i] + z2[i]; t[i] = (u32)c; c >>= 32; }
+    t[8] = (u32)c;
+    c = neg;
+    for (int i = 0; i < 8; i++) { c += (u64)t[i] + (m[i] ^ mask); z1[i] = (u32)c; c >>= 32; }
+    z1[8] = (u32)((u64)t[8] + mask + c);
+    for (int i = 0; i < 4; i++) r[i] = z0[i];
+    c = 0;
+    for (int i = 0; i < 12; i++) {
+        u32 base = (i < 4) ? z0[4 + i] : z2[i - 4];
+        c += (u64)base + (i < 9 ? z1[i] : 0u);
+        r[4 + i] = (u32)c;
+        c >>= 32;
+    }
+#endif
+}
+
+// Measured on B200 (profiles/r1_probes.md): IMAD.WIDE.U32 issues at 32 lanes/clk/SM (one warp instruction per
+// 4 cycles per SM sub-partition), IADD3 at 64 lanes/clk/SM.  Schoolbook: 73 IMAD.WIDE + ~50 other -> bound by
+// the multiplier pipe at ~292 cycles; Karatsuba: 56 IMAD.WIDE + ~170 other -> ~282 cycles when ptxas balances
+// the two pipes, and measured SLOWER (9.8e10 vs 1.09e11 field mults/s).  So the product stays schoolbook and
+// Karatsuba is kept only as a tested alternative.
+SV_HD void u256_mul_wide(u32 r[16], const u32 a[8], const u32 b[8]) { u256_mul_wide_schoolbook(r, a, b); }
+
+// Dedicated squaring: 28 cross products (doubled) + 8 diagonal squares = 36 IMAD.WIDE instead of 64.
 SV_HD void u256_sqr_wide(u32 r[16], const u32 a[8]) {
-    // TODO(perf): dedicated squaring (36 products instead of 64)
-    u256_mul_wide(r, a, a);
+#if SV_DEVICE_CODE
+    // cross products a_i a_j (i<j) accumulated in the even/odd column arrays (O[k] = limb position k+1)
+    u32 E[16], O[16];
+    SV_UNROLL
+    for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
+    // row 0: odd j -> O[0..7] (positions 1,3,5,7), even j -> E[2..7]
+    asm("mul.lo.u32 %0, %8, %9;\n\tmul.hi.u32 %1, %8, %9;\n\t"
+        "mul.lo.u32 %2, %8, %10;\n\tmul.hi.u32 %3, %8, %10;\n\t"
+        "mul.lo.u32 %4, %8, %11;\n\tmul.hi.u32 %5, %8, %11;\n\t"
+        "mul.lo.u32 %6, %8, %12;\n\tmul.hi.u32 %7, %8, %12;"
+        : "=r"(O[0]), "=r"(O[1]), "=r"(O[2]), "=r"(O[3]), "=r"(O[4]), "=r"(O[5]), "=r"(O[6]), "=r"(O[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]));
+    asm("mul.lo.u32 %0, %6, %7;\n\tmul.hi.u32 %1, %6, %7;\n\t"
+        "mul.lo.u32 %2, %6, %8;\n\tmul.hi.u32 %3, %6, %8;\n\t"
+        "mul.lo.u32 %4, %6, %9;\n\tmul.hi.u32 %5, %6, %9;"
+        : "=r"(E[2]), "=r"(E[3]), "=r"(E[4]), "=r"(E[5]), "=r"(E[6]), "=r"(E[7])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]));
+#define SQ_CHAIN3(ACC, X, Y0, Y1, Y2, COUT)                                                          \
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\tmadc.hi.cc.u32 %1, %7, %8, %1;\n\t"                          \
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\tmadc.hi.cc.u32 %3, %7, %9, %3;\n\t"                         \
+        "madc.lo.cc.u32 %4, %7, %10, %4;\n\tmadc.hi.cc.u32 %5, %7, %10, %5;\n\t"                       \
+        "addc.u32 %6, 0, 0;"                                                                          \
+        : "+r"((ACC)[0]), "+r"((ACC)[1]), "+r"((ACC)[2]), "+r"((ACC)[3]), "+r"((ACC)[4]), "+r"((ACC)[5]), "=r"(COUT) \
+        : "r"(X), "r"(Y0), "r"(Y1), "r"(Y2))
+#define SQ_CHAIN2(ACC, X, Y0, Y1, COUT)                                                               \
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\tmadc.hi.cc.u32 %1, %5, %6, %1;\n\t"                          \
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\tmadc.hi.cc.u32 %3, %5, %7, %3;\n\t"                         \
+        "addc.u32 %4, 0, 0;"                                                                          \
+        : "+r"((ACC)[0]), "+r"((ACC)[1]), "+r"((ACC)[2]), "+r"((ACC)[3]), "=r"(COUT)                   \
+        : "r"(X), "r"(Y0), "r"(Y1))
+#define SQ_CHAIN1(ACC, X, Y0, COUT)                                                                   \
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, 0, 0;"        \
+        : "+r"((ACC)[0]), "+r"((ACC)[1]), "=r"(COUT)                                                   \
+        : "r"(X), "r"(Y0))
+    u32 c, dummy;
+    // row 1: even j (2,4,6) -> positions 3,5,7 = O[2..7], carry -> O[8]; odd j (3,5,7) -> positions 4,6,8 = E[4..9]
+    SQ_CHAIN3(O + 2, a[1], a[2], a[4], a[6], c); O[8] = c;
+    SQ_CHAIN3(E + 4, a[1], a[3], a[5], a[7], dummy);
+    // row 2: odd j (3,5,7) -> positions 5,7,9 = O[4..9]; even j (4,6) -> positions 6,8 = E[6..9], carry -> E[10]
+    SQ_CHAIN3(O + 4, a[2], a[3], a[5], a[7], dummy);
+    SQ_CHAIN2(E + 6, a[2], a[4], a[6], c); E[10] = c;
+    // row 3: even j (4,6) -> positions 7,9 = O[6..9], carry -> O[10]; odd j (5,7) -> positions 8,10 = E[8..11]
+    SQ_CHAIN2(O + 6, a[3], a[4], a[6], c); O[10] = c;
+    SQ_CHAIN2(E + 8, a[3], a[5], a[7], dummy);
+    // row 4: odd j (5,7) -> positions 9,11 = O[8..11]; even j (6) -> position 10 = E[10..11], carry -> E[12]
+    SQ_CHAIN2(O + 8, a[4], a[5], a[7], dummy);
+    SQ_CHAIN1(E + 10, a[4], a[6], c); E[12] = c;
+    // row 5: j=6 -> position 11 = O[10..11], carry -> O[12]; j=7 -> position 12 = E[12..13]
+    SQ_CHAIN1(O + 10, a[5], a[6], c); O[12] = c;
+    SQ_CHAIN1(E + 12, a[5], a[7], dummy);
+    // row 6: j=7 -> position 13 = O[12..13]
+    SQ_CHAIN1(O + 12, a[6], a[7], dummy);
+    (void)dummy;
+#undef SQ_CHAIN3
+#undef SQ_CHAIN2
+#undef SQ_CHAIN1
+    // S = E + (O << 32): cross-product sum, limbs 1..15
+    u32 S[16];
+    sv_merge16(S, E, O);  // S[0] = E[0] = 0
+    // D = sum a_i^2 2^(64 i): eight independent products
+    u32 D[16];
+    asm("mul.lo.u32 %0, %8, %8;\n\tmul.hi.u32 %1, %8, %8;\n\t"
+        "mul.lo.u32 %2, %9, %9;\n\tmul.hi.u32 %3, %9, %9;\n\t"
+        "mul.lo.u32 %4, %10, %10;\n\tmul.hi.u32 %5, %10, %10;\n\t"
+        "mul.lo.u32 %6, %11, %11;\n\tmul.hi.u32 %7, %11, %11;"
+        : "=r"(D[0]), "=r"(D[1]), "=r"(D[2]), "=r"(D[3]), "=r"(D[4]), "=r"(D[5]), "=r"(D[6]), "=r"(D[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]));
+    asm("mul.lo.u32 %0, %8, %8;\n\tmul.hi.u32 %1, %8, %8;\n\t"
+        "mul.lo.u32 %2, %9, %9;\n\tmul.hi.u32 %3, %9, %9;\n\t"
+        "mul.lo.u32 %4, %10, %10;\n\tmul.hi.u32 %5, %10, %10;\n\t"
+        "mul.lo.u32 %6, %11, %11;\n\tmul.hi.u32 %7, %11, %11;"
+        : "=r"(D[8]), "=r"(D[9]), "=r"(D[10]), "=r"(D[11]), "=r"(D[12]), "=r"(D[13]), "=r"(D[14]), "=r"(D[15])
+        : "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+    // r = D + 2 S   (two add chains; S[0] == 0)
+    u32 T[16];
+    T[0] = D[0];
+#define ADD15(OUT, X, Y)                                                                               \
+    asm("add.cc.u32 %0, %15, %30;\n\t"                                                                 \
+        "addc.cc.u32 %1, %16, %31;\n\taddc.cc.u32 %2, %17, %32;\n\taddc.cc.u32 %3, %18, %33;\n\t"      \
+        "addc.cc.u32 %4, %19, %34;\n\taddc.cc.u32 %5, %20, %35;\n\taddc.cc.u32 %6, %21, %36;\n\t"      \
+        "addc.cc.u32 %7, %22, %37;\n\taddc.cc.u32 %8, %23, %38;\n\taddc.cc.u32 %9, %24, %39;\n\t"      \
+        "addc.cc.u32 %10, %25, %40;\n\taddc.cc.u32 %11, %26, %41;\n\taddc.cc.u32 %12, %27, %42;\n\t"   \
+        "addc.cc.u32 %13, %28, %43;\n\taddc.u32 %14, %29, %44;"                                        \
+        : "=r"((OUT)[1]), "=r"((OUT)[2]), "=r"((OUT)[3]), "=r"((OUT)[4]), "=r"((OUT)[5]), "=r"((OUT)[6]),     \
+          "=r"((OUT)[7]), "=r"((OUT)[8]), "=r"((OUT)[9]), "=r"((OUT)[10]), "=r"((OUT)[11]), "=r"((OUT)[12]),  \
+          "=r"((OUT)[13]), "=r"((OUT)[14]), "=r"((OUT)[15])                                                   \
+        : "r"((X)[1]), "r"((X)[2]), "r"((X)[3]), "r"((X)[4]), "r"((X)[5]), "r"((X)[6]), "r"((X)[7]), "r"((X)[8]), \
+          "r"((X)[9]), "r"((X)[10]), "r"((X)[11]), "r"((X)[12]), "r"((X)[13]), "r"((X)[14]), "r"((X)[15]),     \
+          "r"((Y)[1]), "r"((Y)[2]), "r"((Y)[3]), "r"((Y)[4]), "r"((Y)[5]), "r"((Y)[6]), "r"((Y)[7]), "r"((Y)[8]), \
+          "r"((Y)[9]), "r"((Y)[10]), "r"((Y)[11]), "r"((Y)[12]), "r"((Y)[13]), "r"((Y)[14]), "r"((Y)[15]))
+    ADD15(T, D, S);
+    r[0] = T[0];
+    ADD15(r, T, S);
+#undef ADD15
+#else
+    u256_mul_wide_schoolbook(r, a, a);
+#endif
 }

@@ -49,6 +49,10 @@ def load_library():
     lib.sv_verify_host_raw.argtypes = [vp, i, vp, sz, vp, vp, vp, vp, sz, vp]
     lib.sv_verify_device.argtypes = [vp, i, vp, vp, vp, sz, vp, vp, vp]
     lib.sv_sync.argtypes = [vp, vp]
+    lib.sv_get_stream.argtypes = [vp]
+    lib.sv_set_profiling.argtypes = [vp, i]
+    lib.sv_get_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    lib.sv_get_stream.restype = vp
     lib.sv_enqueue.argtypes = [vp, i, vp, vp, vp]
     lib.sv_enqueue.restype = ctypes.c_long
     lib.sv_pending.argtypes = [vp]
@@ -192,8 +196,37 @@ class SigVerifier:
         self._check(self.lib.sv_synth_device(self._ctx, kind, seed, n, d_msg, d_key, d_sig, stream or None),
                     "sv_synth_device")
 
+    def stream_handle(self):
+        """cudaStream_t of the context's own stream (wrap with torch.cuda.ExternalStream to time on it)."""
+        return self.lib.sv_get_stream(self._ctx)
+
     def sync(self, stream=0):
         self._check(self.lib.sv_sync(self._ctx, stream or None), "sv_sync")
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.sv_set_profiling(self._ctx, 1 if on else 0), "sv_set_profiling")
+
+    def last_timing(self):
+        """(prep_ms, main_ms) device time of the last verify launch pair; call after sync()."""
+        a, b = ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.sv_get_last_timing(self._ctx, ctypes.byref(a), ctypes.byref(b)), "sv_get_last_timing")
+        return a.value, b.value
+
+    def host_alloc(self, nbytes):
+        """Pinned host buffer as a numpy uint8 array (cudaHostAlloc); free with host_free(arr)."""
+        p = self.lib.sv_host_alloc(nbytes)
+        if not p:
+            raise EngineError("sv_host_alloc failed")
+        buf = (ctypes.c_uint8 * nbytes).from_address(p)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr):
+        p = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if p:
+            self.lib.sv_host_free(p)
 
     def info(self):
         inf = SvInfo()

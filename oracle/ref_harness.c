@@ -152,3 +152,60 @@ void ref_sha256d(const uint8_t *p, size_t len, uint8_t *out32) {
 void ref_tagged_sha256(const uint8_t *tag, size_t taglen, const uint8_t *msg, size_t msglen, uint8_t *out32) {
     secp256k1_tagged_sha256(ctx(), out32, tag, taglen, msg, msglen);
 }
+
+/* ---- seeded workload for bench.py's reference arm (SURVEY.md §8(d) C2 recipe): SplitMix64 secret
+ * keys and message hashes, signed with the reference's RFC6979 signer (low-S by construction); every
+ * 10th item corrupted, classes round-robin {msg bit, r bit, s bit, high-S, neighbour's key,
+ * non-residue x, prefix 0x04}.  Generation is untimed. ---- */
+static uint64_t splitmix(uint64_t *s) {
+    uint64_t z = (*s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+typedef struct { uint64_t seed; size_t lo, hi; uint8_t *msg, *pub, *sig; } gen_t;
+static void *gen_worker(void *arg) {
+    gen_t *g = (gen_t *)arg;
+    for (size_t i = g->lo; i < g->hi; i++) {
+        uint64_t st = g->seed ^ (0xD1B54A32D192ED03ULL * (i + 1));
+        uint8_t sk[32];
+        for (int k = 0; k < 4; k++) { uint64_t v = splitmix(&st); memcpy(sk + 8 * k, &v, 8); }
+        for (int k = 0; k < 4; k++) { uint64_t v = splitmix(&st); memcpy(g->msg + 32 * i + 8 * k, &v, 8); }
+        sk[0] &= 0x7f; sk[31] |= 1; /* 0 < sk < n */
+        ref_pubkey_create(sk, g->pub + 33 * i, NULL);
+        ref_ecdsa_sign(sk, g->msg + 32 * i, g->sig + 64 * i);
+    }
+    return NULL;
+}
+void ref_make_ecdsa_batch(uint64_t seed, size_t n, uint8_t *msg, uint8_t *pub33, uint8_t *sig, int nthreads) {
+    (void)ctx();
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    gen_t *jobs = (gen_t *)malloc(sizeof(gen_t) * (size_t)nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (gen_t){seed, n * (size_t)t / (size_t)nthreads, n * (size_t)(t + 1) / (size_t)nthreads, msg, pub33, sig};
+        pthread_create(&th[t], NULL, gen_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+    static const uint8_t order[32] = {0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFE,
+                                      0xBA,0xAE,0xDC,0xE6,0xAF,0x48,0xA0,0x3B,0xBF,0xD2,0x5E,0x8C,0xD0,0x36,0x41,0x41};
+    for (size_t i = 0, cls = 0; i < n; i += 10, cls++) {
+        size_t j = (i + 1) % n;
+        switch (cls % 7) {
+        case 0: msg[32 * i + 5] ^= 4; break;
+        case 1: sig[64 * i + 7] ^= 1; break;
+        case 2: sig[64 * i + 40] ^= 1; break;
+        case 3: { /* s <- n - s */
+            int borrow = 0;
+            for (int k = 31; k >= 0; k--) {
+                int d = (int)order[k] - (int)sig[64 * i + 32 + k] - borrow;
+                borrow = d < 0; sig[64 * i + 32 + k] = (uint8_t)(d + (borrow << 8));
+            }
+            break; }
+        case 4: memcpy(pub33 + 33 * i, pub33 + 33 * j, 33); break;
+        case 5: memset(pub33 + 33 * i + 1, 0, 32); pub33[33 * i + 32] = 5; break; /* x = 5: 5^3+7 is a non-residue */
+        case 6: pub33[33 * i] = 4; break;
+        }
+    }
+}

@@ -1,0 +1,176 @@
+"""CPU-only: the engine's device headers compiled for the host (tests/host_emul) vs Python integers,
+the oracle and the golden vectors.  Everything above the inline-PTX primitives is covered here; the
+PTX forms of those primitives are covered by the -m gpu tests."""
+import ctypes
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests import adversarial, util
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+P = util.P
+p, n = util.P_FIELD, util.N_ORDER
+LAM = adversarial.LAMBDA
+
+
+def L(x):
+    return (ctypes.c_uint32 * 8)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
+def V(a, k=8):
+    return sum(int(a[i]) << (32 * i) for i in range(k))
+
+
+def feop(E, op, a, b=0):
+    o = (ctypes.c_uint32 * 8)()
+    E.emul_fe_op(op, L(a), L(b), o)
+    return V(o)
+
+
+def scop(E, op, a, b=0):
+    o = (ctypes.c_uint32 * 8)()
+    E.emul_sc_op(op, L(a), L(b), o)
+    return V(o)
+
+
+EDGE = [0, 1, 2, p - 1, p, p + 1, 2**256 - 1, 2**256 - 2, 2**32 + 977, 2**32 + 976, 2**255, p - 2, (p + 1) // 2,
+        2**224, 977, 2**256 - 2**32 - 978, 2**64 - 1, (2**256 - 1) ^ (2**128 - 1)]
+
+
+def test_field_ops_vs_python(emul):
+    rnd = random.Random(1)
+    vals = EDGE + [rnd.getrandbits(256) for _ in range(120)]
+    for a in vals:
+        for b in rnd.sample(vals, 10) + EDGE[:9]:
+            assert feop(emul, 0, a, b) == a * b % p
+            assert feop(emul, 2, a, b) == (a + b) % p
+            assert feop(emul, 3, a, b) == (a - b) % p
+            raw = (ctypes.c_uint32 * 8)()
+            for op in (0, 2, 3):  # weak form: any value < 2^256 congruent to the result
+                emul.emul_fe_op_raw(op, L(a), L(b), raw)
+                exp = [a * b, 0, a + b, a - b][op]
+                assert V(raw) % p == exp % p
+        assert feop(emul, 1, a) == a * a % p
+        assert feop(emul, 6, a) == (-a) % p
+        for k in (2, 3, 8, 65535):
+            assert feop(emul, 7, a, k) == k * a % p
+    for a in vals[:50]:
+        assert feop(emul, 4, a) == pow(a, p - 2, p)
+        s = feop(emul, 5, a)
+        if pow(a % p, (p - 1) // 2, p) in (0, 1):
+            assert s * s % p == a % p
+        else:
+            assert s == 0
+
+
+def test_scalar_ops_vs_python(emul):
+    rnd = random.Random(2)
+    vals = [0, 1, 2, n - 1, n - 2, (n - 1) // 2, (n + 1) // 2, 2**128, 2**255] + [rnd.randrange(n) for _ in range(80)]
+    for a in vals:
+        for b in rnd.sample(vals, 8):
+            assert scop(emul, 0, a, b) == a * b % n
+            assert scop(emul, 2, a, b) == (a + b) % n
+        assert scop(emul, 3, a) == (-a) % n
+    for a in vals[:16]:
+        assert scop(emul, 1, a) == pow(a, n - 2, n)
+    for i in range(150):
+        t = [2**512 - 1, 0, 2**256, n * n, (n - 1) ** 2, 2**512 - 2**256][i] if i < 6 else rnd.getrandbits(512)
+        arr = (ctypes.c_uint32 * 16)(*[(t >> (32 * k)) & 0xFFFFFFFF for k in range(16)])
+        o = (ctypes.c_uint32 * 8)()
+        emul.emul_sc_reduce512(arr, o)
+        assert V(o) == t % n
+
+
+def test_glv_split_and_recoding_invariants(emul):
+    rnd = random.Random(3)
+    specials = [v % n for v in adversarial.special_scalars()]
+    for u2 in specials + [rnd.randrange(n) for _ in range(300)]:
+        u1 = rnd.choice(specials) if u2 & 1 else rnd.randrange(n)
+        k1 = (ctypes.c_uint32 * 5)()
+        k2 = (ctypes.c_uint32 * 5)()
+        gd = (ctypes.c_int * 16)()
+        emul.emul_prepare(L(u1), L(u2), k1, k2, gd)
+        a, b = V(k1, 5), V(k2, 5)
+        sa, sb = a >> 159, b >> 159
+        a &= (1 << 159) - 1
+        b &= (1 << 159) - 1
+        assert a & 1 and b & 1 and a < 2**131 and b < 2**131  # odd halves, top window value <= 7
+        A, B = (-a if sa else a), (-b if sb else b)
+        assert (A + B * LAM - u2) % n == 0
+        assert sum(gd[i] << (16 * i) for i in range(16)) == u1
+        assert all(-32768 <= gd[i] <= 32768 for i in range(15)) and 0 <= gd[15] <= 65536
+
+
+def test_device_sha256_paths(emul):
+    import hashlib
+    rnd = np.random.default_rng(4)
+    for ln in [0, 1, 55, 56, 63, 64, 65, 119, 120, 127, 128, 174, 1000]:
+        d = rnd.integers(0, 256, size=max(ln, 1), dtype=np.uint8)
+        o = np.zeros(32, np.uint8)
+        emul.emul_sha256d(P(d), ctypes.c_size_t(ln), P(o))
+        assert bytes(o) == hashlib.sha256(hashlib.sha256(bytes(d[:ln])).digest()).digest(), ln
+    tag = hashlib.sha256(b"BIP0340/challenge").digest()
+    for _ in range(5):
+        r, px, m = (rnd.integers(0, 256, size=32, dtype=np.uint8) for _ in range(3))
+        o = np.zeros(32, np.uint8)
+        emul.emul_bip340_challenge(P(r), P(px), P(m), P(o))
+        assert bytes(o) == hashlib.sha256(tag + tag + bytes(r) + bytes(px) + bytes(m)).digest()
+
+
+def test_gtable_entries(emul, ref):
+    emul.emul_gtable_build()
+    for row, d in [(0, 1), (0, 2), (0, 32768), (1, 1), (7, 12345), (15, 65536), (15, 1), (14, 32768), (3, 77)]:
+        e = row * 32768 + d - 1
+        xy = (ctypes.c_uint32 * 16)()
+        emul.emul_gtable_get(e, xy)
+        k = (d << (16 * row)) % n
+        kb = np.frombuffer(k.to_bytes(32, "big"), dtype=np.uint8).copy()
+        out = np.zeros(64, np.uint8)
+        assert ref.ref_scalar_base_mult(P(kb), P(out))
+        assert V(xy[:8]).to_bytes(32, "big") + V(xy[8:]).to_bytes(32, "big") == bytes(out)
+        xy2 = (ctypes.c_uint32 * 16)()
+        emul.emul_gtable_entry_device_algo(e, xy2)  # the double-and-add + Fermat path the K4 kernel uses
+        assert list(xy) == list(xy2)
+
+
+def emul_verify(emul, kind, msg, key, sig):
+    out = np.zeros(msg.shape[0], np.uint8)
+    msg, key, sig = (np.ascontiguousarray(a) for a in (msg, key, sig))
+    emul.emul_verify_batch(kind, P(msg), P(key), P(sig), ctypes.c_size_t(msg.shape[0]), P(out))
+    return out
+
+
+def test_full_verify_random_and_corrupted(emul, ref):
+    w = util.corrupt(util.make_signed(ref, 700, seed=5), every=3)
+    for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ssig")]):
+        want = util.ref_verify(ref, kind, w["msg"], w[k], w[s])
+        assert np.array_equal(emul_verify(emul, kind, w["msg"], w[k], w[s]), want), kind
+
+
+def test_full_verify_golden_vectors(emul):
+    h = lambda s, k: np.frombuffer(bytes.fromhex(s), dtype=np.uint8).reshape(1, k).copy()
+    for v in json.load(open(os.path.join(GOLD, "wycheproof_ecdsa.json"))):
+        if v["sig64"] is None:
+            continue
+        assert emul_verify(emul, 0, h(v["msg32"], 32), h(v["pub33"], 33), h(v["sig64"], 64))[0] == v["expected"], v["tcId"]
+        assert emul_verify(emul, 1, h(v["msg32"], 32), h(v["pubxy"], 64), h(v["sig64"], 64))[0] == v["expected"], v["tcId"]
+    for v in json.load(open(os.path.join(GOLD, "bip340.json"))):
+        assert emul_verify(emul, 2, h(v["msg32"], 32), h(v["xonly"], 32), h(v["sig64"], 64))[0] == v["expected"], v["index"]
+
+
+def test_full_verify_adversarial_scalars(emul, ref):
+    msg, pub33, pubxy, sig = adversarial.cases()
+    assert msg.shape[0] > 500
+    want = util.ref_verify(ref, 0, msg, pub33, sig)
+    assert want.all(), "crafted signatures must be valid under the reference"
+    assert np.array_equal(emul_verify(emul, 0, msg, pub33, sig), want)
+    assert np.array_equal(emul_verify(emul, 1, msg, pubxy, sig), want)
+    # and the same signatures against a wrong message must fail identically
+    msg2 = msg.copy()
+    msg2[:, 31] ^= 1
+    want2 = util.ref_verify(ref, 0, msg2, pub33, sig)
+    assert np.array_equal(emul_verify(emul, 0, msg2, pub33, sig), want2)
