@@ -37,12 +37,19 @@ def _sources(d, exts):
 
 
 def build_engine(force=False, verbose=False, extra_flags=()):
-    srcs = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "cln_sigverify.h")]
+    srcs = _sources(CSRC, (".cu", ".cuh", ".c")) + [os.path.join(ROOT, "include", "cln_sigverify.h"),
+                                                   os.path.join(ROOT, "include", "cln_dropin.h")]
     if not force and _newer(LIB, srcs):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    # host side of the drop-in is plain C (as the reference's bitcoin/signature.c), compiled by gcc
+    dropin_o = os.path.join(CSRC, "cln_dropin.o")
+    r = subprocess.run(["gcc", "-O2", "-fPIC", "-Wall", "-Wextra", "-std=c11", "-c", os.path.join(CSRC, "cln_dropin.c"),
+                        "-o", dropin_o], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc (cln_dropin.c) failed:\n" + r.stdout + r.stderr)
     cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB, os.path.join(CSRC, "engine.cu")]
+        "-o", LIB, os.path.join(CSRC, "engine.cu"), dropin_o]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

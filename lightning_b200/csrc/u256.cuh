@@ -10,6 +10,7 @@
 // Host path (tests/host_emul only): plain uint64_t arithmetic with identical semantics.
 #pragma once
 #include "common.cuh"
+#include "u256_gen.cuh"  // generated PTX bodies: sv_mul8_dev, sv_sqr8_dev (tools/gen_mul.py)
 
 // ---------------------------------------------------------------------------------------------
 // add / sub with carry, 8 limbs
@@ -131,20 +132,7 @@ SV_D void sv_merge16(u32 r[16], const u32 e[16], const u32 o[16]) {
 // the scalar-field code; the field code uses the Karatsuba / dedicated-square versions below.
 SV_HD void u256_mul_wide_schoolbook(u32 r[16], const u32 a[8], const u32 b[8]) {
 #if SV_DEVICE_CODE
-    // E holds products whose low limb sits at an even position, O those at an odd position
-    // (O[k] is limb position k+1).  Zero-initialised; ptxas folds the zeros into RZ operands.
-    u32 E[18], O[18];
-    SV_UNROLL
-    for (int i = 0; i < 18; i++) { E[i] = 0; O[i] = 0; }
-    SV_UNROLL
-    for (int i = 0; i < 8; i++) {
-        u32* A = (i & 1) ? (O + i - 1) : (E + i);  // a[even j] * b[i] -> position i+j (parity of i)
-        u32* B = (i & 1) ? (E + i + 1) : (O + i);  // a[odd j]  * b[i] -> position i+j (parity of i+1)
-        u32 c = sv_cmad4(A, a[0], a[2], a[4], a[6], b[i]);
-        A[8] = c;  // limb i+8 of that array is still untouched at this point
-        (void)sv_cmad4(B, a[1], a[3], a[5], a[7], b[i]);  // top product lands on fresh limbs: no carry-out
-    }
-    sv_merge16(r, E, O);
+    sv_mul8_dev(r, a, b);
 #else
     u64 t[16];
     for (int i = 0; i < 16; i++) t[i] = 0;
@@ -348,99 +336,7 @@ SV_HD void u256_mul_wide(u32 r[16], const u32 a[8], const u32 b[8]) { u256_mul_w
 // Dedicated squaring: 28 cross products (doubled) + 8 diagonal squares = 36 IMAD.WIDE instead of 64.
 SV_HD void u256_sqr_wide(u32 r[16], const u32 a[8]) {
 #if SV_DEVICE_CODE
-    // cross products a_i a_j (i<j) accumulated in the even/odd column arrays (O[k] = limb position k+1)
-    u32 E[16], O[16];
-    SV_UNROLL
-    for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
-    // row 0: odd j -> O[0..7] (positions 1,3,5,7), even j -> E[2..7]
-    asm("mul.lo.u32 %0, %8, %9;\n\tmul.hi.u32 %1, %8, %9;\n\t"
-        "mul.lo.u32 %2, %8, %10;\n\tmul.hi.u32 %3, %8, %10;\n\t"
-        "mul.lo.u32 %4, %8, %11;\n\tmul.hi.u32 %5, %8, %11;\n\t"
-        "mul.lo.u32 %6, %8, %12;\n\tmul.hi.u32 %7, %8, %12;"
-        : "=r"(O[0]), "=r"(O[1]), "=r"(O[2]), "=r"(O[3]), "=r"(O[4]), "=r"(O[5]), "=r"(O[6]), "=r"(O[7])
-        : "r"(a[0]), "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]));
-    asm("mul.lo.u32 %0, %6, %7;\n\tmul.hi.u32 %1, %6, %7;\n\t"
-        "mul.lo.u32 %2, %6, %8;\n\tmul.hi.u32 %3, %6, %8;\n\t"
-        "mul.lo.u32 %4, %6, %9;\n\tmul.hi.u32 %5, %6, %9;"
-        : "=r"(E[2]), "=r"(E[3]), "=r"(E[4]), "=r"(E[5]), "=r"(E[6]), "=r"(E[7])
-        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]));
-#define SQ_CHAIN3(ACC, X, Y0, Y1, Y2, COUT)                                                          \
-    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\tmadc.hi.cc.u32 %1, %7, %8, %1;\n\t"                          \
-        "madc.lo.cc.u32 %2, %7, %9, %2;\n\tmadc.hi.cc.u32 %3, %7, %9, %3;\n\t"                         \
-        "madc.lo.cc.u32 %4, %7, %10, %4;\n\tmadc.hi.cc.u32 %5, %7, %10, %5;\n\t"                       \
-        "addc.u32 %6, 0, 0;"                                                                          \
-        : "+r"((ACC)[0]), "+r"((ACC)[1]), "+r"((ACC)[2]), "+r"((ACC)[3]), "+r"((ACC)[4]), "+r"((ACC)[5]), "=r"(COUT) \
-        : "r"(X), "r"(Y0), "r"(Y1), "r"(Y2))
-#define SQ_CHAIN2(ACC, X, Y0, Y1, COUT)                                                               \
-    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\tmadc.hi.cc.u32 %1, %5, %6, %1;\n\t"                          \
-        "madc.lo.cc.u32 %2, %5, %7, %2;\n\tmadc.hi.cc.u32 %3, %5, %7, %3;\n\t"                         \
-        "addc.u32 %4, 0, 0;"                                                                          \
-        : "+r"((ACC)[0]), "+r"((ACC)[1]), "+r"((ACC)[2]), "+r"((ACC)[3]), "=r"(COUT)                   \
-        : "r"(X), "r"(Y0), "r"(Y1))
-#define SQ_CHAIN1(ACC, X, Y0, COUT)                                                                   \
-    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, 0, 0;"        \
-        : "+r"((ACC)[0]), "+r"((ACC)[1]), "=r"(COUT)                                                   \
-        : "r"(X), "r"(Y0))
-    u32 c, dummy;
-    // row 1: even j (2,4,6) -> positions 3,5,7 = O[2..7], carry -> O[8]; odd j (3,5,7) -> positions 4,6,8 = E[4..9]
-    SQ_CHAIN3(O + 2, a[1], a[2], a[4], a[6], c); O[8] = c;
-    SQ_CHAIN3(E + 4, a[1], a[3], a[5], a[7], dummy);
-    // row 2: odd j (3,5,7) -> positions 5,7,9 = O[4..9]; even j (4,6) -> positions 6,8 = E[6..9], carry -> E[10]
-    SQ_CHAIN3(O + 4, a[2], a[3], a[5], a[7], dummy);
-    SQ_CHAIN2(E + 6, a[2], a[4], a[6], c); E[10] = c;
-    // row 3: even j (4,6) -> positions 7,9 = O[6..9], carry -> O[10]; odd j (5,7) -> positions 8,10 = E[8..11]
-    SQ_CHAIN2(O + 6, a[3], a[4], a[6], c); O[10] = c;
-    SQ_CHAIN2(E + 8, a[3], a[5], a[7], dummy);
-    // row 4: odd j (5,7) -> positions 9,11 = O[8..11]; even j (6) -> position 10 = E[10..11], carry -> E[12]
-    SQ_CHAIN2(O + 8, a[4], a[5], a[7], dummy);
-    SQ_CHAIN1(E + 10, a[4], a[6], c); E[12] = c;
-    // row 5: j=6 -> position 11 = O[10..11], carry -> O[12]; j=7 -> position 12 = E[12..13]
-    SQ_CHAIN1(O + 10, a[5], a[6], c); O[12] = c;
-    SQ_CHAIN1(E + 12, a[5], a[7], dummy);
-    // row 6: j=7 -> position 13 = O[12..13]
-    SQ_CHAIN1(O + 12, a[6], a[7], dummy);
-    (void)dummy;
-#undef SQ_CHAIN3
-#undef SQ_CHAIN2
-#undef SQ_CHAIN1
-    // S = E + (O << 32): cross-product sum, limbs 1..15
-    u32 S[16];
-    sv_merge16(S, E, O);  // S[0] = E[0] = 0
-    // D = sum a_i^2 2^(64 i): eight independent products
-    u32 D[16];
-    asm("mul.lo.u32 %0, %8, %8;\n\tmul.hi.u32 %1, %8, %8;\n\t"
-        "mul.lo.u32 %2, %9, %9;\n\tmul.hi.u32 %3, %9, %9;\n\t"
-        "mul.lo.u32 %4, %10, %10;\n\tmul.hi.u32 %5, %10, %10;\n\t"
-        "mul.lo.u32 %6, %11, %11;\n\tmul.hi.u32 %7, %11, %11;"
-        : "=r"(D[0]), "=r"(D[1]), "=r"(D[2]), "=r"(D[3]), "=r"(D[4]), "=r"(D[5]), "=r"(D[6]), "=r"(D[7])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]));
-    asm("mul.lo.u32 %0, %8, %8;\n\tmul.hi.u32 %1, %8, %8;\n\t"
-        "mul.lo.u32 %2, %9, %9;\n\tmul.hi.u32 %3, %9, %9;\n\t"
-        "mul.lo.u32 %4, %10, %10;\n\tmul.hi.u32 %5, %10, %10;\n\t"
-        "mul.lo.u32 %6, %11, %11;\n\tmul.hi.u32 %7, %11, %11;"
-        : "=r"(D[8]), "=r"(D[9]), "=r"(D[10]), "=r"(D[11]), "=r"(D[12]), "=r"(D[13]), "=r"(D[14]), "=r"(D[15])
-        : "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
-    // r = D + 2 S   (two add chains; S[0] == 0)
-    u32 T[16];
-    T[0] = D[0];
-#define ADD15(OUT, X, Y)                                                                               \
-    asm("add.cc.u32 %0, %15, %30;\n\t"                                                                 \
-        "addc.cc.u32 %1, %16, %31;\n\taddc.cc.u32 %2, %17, %32;\n\taddc.cc.u32 %3, %18, %33;\n\t"      \
-        "addc.cc.u32 %4, %19, %34;\n\taddc.cc.u32 %5, %20, %35;\n\taddc.cc.u32 %6, %21, %36;\n\t"      \
-        "addc.cc.u32 %7, %22, %37;\n\taddc.cc.u32 %8, %23, %38;\n\taddc.cc.u32 %9, %24, %39;\n\t"      \
-        "addc.cc.u32 %10, %25, %40;\n\taddc.cc.u32 %11, %26, %41;\n\taddc.cc.u32 %12, %27, %42;\n\t"   \
-        "addc.cc.u32 %13, %28, %43;\n\taddc.u32 %14, %29, %44;"                                        \
-        : "=r"((OUT)[1]), "=r"((OUT)[2]), "=r"((OUT)[3]), "=r"((OUT)[4]), "=r"((OUT)[5]), "=r"((OUT)[6]),     \
-          "=r"((OUT)[7]), "=r"((OUT)[8]), "=r"((OUT)[9]), "=r"((OUT)[10]), "=r"((OUT)[11]), "=r"((OUT)[12]),  \
-          "=r"((OUT)[13]), "=r"((OUT)[14]), "=r"((OUT)[15])                                                   \
-        : "r"((X)[1]), "r"((X)[2]), "r"((X)[3]), "r"((X)[4]), "r"((X)[5]), "r"((X)[6]), "r"((X)[7]), "r"((X)[8]), \
-          "r"((X)[9]), "r"((X)[10]), "r"((X)[11]), "r"((X)[12]), "r"((X)[13]), "r"((X)[14]), "r"((X)[15]),     \
-          "r"((Y)[1]), "r"((Y)[2]), "r"((Y)[3]), "r"((Y)[4]), "r"((Y)[5]), "r"((Y)[6]), "r"((Y)[7]), "r"((Y)[8]), \
-          "r"((Y)[9]), "r"((Y)[10]), "r"((Y)[11]), "r"((Y)[12]), "r"((Y)[13]), "r"((Y)[14]), "r"((Y)[15]))
-    ADD15(T, D, S);
-    r[0] = T[0];
-    ADD15(r, T, S);
-#undef ADD15
+    sv_sqr8_dev(r, a);
 #else
     u256_mul_wide_schoolbook(r, a, a);
 #endif

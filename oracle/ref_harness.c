@@ -209,3 +209,31 @@ void ref_make_ecdsa_batch(uint64_t seed, size_t n, uint8_t *msg, uint8_t *pub33,
         }
     }
 }
+
+/* ---- opaque libsecp256k1 structs for the drop-in tests (what CLN's wire parsers hand to check_signed_hash) ---- */
+int ref_make_opaque_pubkey(const uint8_t *pub33, uint8_t *opaque64) {
+    secp256k1_pubkey pk;
+    if (!secp256k1_ec_pubkey_parse(ctx(), &pk, pub33, 33)) return 0;
+    memcpy(opaque64, pk.data, 64);
+    return 1;
+}
+int ref_make_opaque_sig(const uint8_t *sig64, uint8_t *opaque64) {
+    secp256k1_ecdsa_signature s;
+    if (!secp256k1_ecdsa_signature_parse_compact(ctx(), &s, sig64)) return 0;
+    memcpy(opaque64, s.data, 64);
+    return 1;
+}
+/* reference verdicts on opaque inputs: secp256k1_ecdsa_verify as bitcoin/signature.c:174 calls it, and
+ * check_schnorr_sig's serialize -> drop parity -> xonly_parse -> schnorrsig_verify (signature.c:408-430) */
+int ref_check_signed_hash_opaque(const uint8_t *hash32, const uint8_t *sig_opaque64, const uint8_t *pub_opaque64) {
+    secp256k1_pubkey pk; secp256k1_ecdsa_signature s;
+    memcpy(pk.data, pub_opaque64, 64); memcpy(s.data, sig_opaque64, 64);
+    return secp256k1_ecdsa_verify(ctx(), &s, hash32, &pk);
+}
+int ref_check_schnorr_sig_opaque(const uint8_t *hash32, const uint8_t *pub_opaque64, const uint8_t *sig64) {
+    secp256k1_pubkey pk; secp256k1_xonly_pubkey xo; uint8_t ser[33]; size_t l = 33;
+    memcpy(pk.data, pub_opaque64, 64);
+    if (!secp256k1_ec_pubkey_serialize(ctx(), ser, &l, &pk, SECP256K1_EC_COMPRESSED)) return -1;
+    if (!secp256k1_xonly_pubkey_parse(ctx(), &xo, ser + 1)) return -1;
+    return secp256k1_schnorrsig_verify(ctx(), sig64, hash32, 32, &xo);
+}

@@ -1,0 +1,207 @@
+"""GPU: the engine against the committed golden vectors, the drop-in (CLN-signature) entry points,
+and size-independent properties at the benchmark's full batch size."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import adversarial, gossip, util
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+P = util.P
+
+
+def _rows(vec, field, n):
+    return np.stack([np.frombuffer(bytes.fromhex(v[field]), dtype=np.uint8) for v in vec]).reshape(len(vec), n)
+
+
+def test_wycheproof_ecdsa(engine):
+    vec = [v for v in json.load(open(os.path.join(GOLD, "wycheproof_ecdsa.json"))) if v["sig64"] is not None]
+    assert len(vec) == 273
+    want = np.array([v["expected"] for v in vec], np.uint8)
+    msg, sig = _rows(vec, "msg32", 32), _rows(vec, "sig64", 64)
+    assert np.array_equal(engine.verify(0, msg, _rows(vec, "pub33", 33), sig), want)
+    assert np.array_equal(engine.verify(1, msg, _rows(vec, "pubxy", 64), sig), want)
+
+
+def test_bip340(engine):
+    vec = json.load(open(os.path.join(GOLD, "bip340.json")))
+    want = np.array([v["expected"] for v in vec], np.uint8)
+    got = engine.verify(2, _rows(vec, "msg32", 32), _rows(vec, "xonly", 32), _rows(vec, "sig64", 64))
+    assert np.array_equal(got, want)
+
+
+def test_pubkey_parse_tables(engine):
+    vec = [v for v in json.load(open(os.path.join(GOLD, "pubkey_parse.json"))) if "pub33" in v]
+    xy, ok = engine.pubkey_parse(_rows(vec, "pub33", 33))
+    for i, v in enumerate(vec):
+        assert bool(ok[i]) == bool(v["expected"]), v
+        if v["expected"]:
+            assert bytes(xy[i]).hex() == v["xy"]
+
+
+def test_adversarial_scalars(engine, ref):
+    msg, pub33, pubxy, sig = adversarial.load()
+    want = util.ref_verify(ref, 0, msg, pub33, sig)
+    assert want.all()
+    assert np.array_equal(engine.verify(0, msg, pub33, sig), want)
+    assert np.array_equal(engine.verify(1, msg, pubxy, sig), want)
+    msg2 = msg.copy()
+    msg2[:, 31] ^= 1
+    assert np.array_equal(engine.verify(0, msg2, pub33, sig), util.ref_verify(ref, 0, msg2, pub33, sig))
+
+
+def test_gossip_replay_device_hashing(engine, ref):
+    """config C4 in miniature: the mainnet gossip fixture tiled x7, device-side SHA-256d of msg[258:] / msg[66:],
+    ~1 % of messages bit-flipped; every verdict diffed against the reference run on the same bytes."""
+    msgs = gossip.load_subset() * 7
+    data, off, ln, key, sig, owner, which = gossip.items_of(msgs)
+    rng = np.random.default_rng(1)
+    flip = rng.choice(len(msgs), size=len(msgs) // 100, replace=False)
+    starts = np.cumsum([0] + [len(m) for m in msgs])[:-1]
+    for mi in flip:
+        pos = int(starts[mi]) + int(rng.integers(2, len(msgs[mi])))
+        data[pos] ^= 1 << int(rng.integers(0, 8))
+    got = engine.verify_raw(0, data, off, ln, key, sig)
+    # reference: hash each span with CCAN sha256 (sha256_double), then parse + verify
+    h = np.zeros((off.size, 32), np.uint8)
+    for i in range(off.size):
+        seg = np.ascontiguousarray(data[int(off[i]):int(off[i]) + int(ln[i])])
+        ref.ref_sha256d(P(seg), ctypes.c_size_t(seg.size), P(h[i]))
+    # sigs/keys may have been hit by the flips too: re-slice them from the mutated bytes
+    data2, off2, ln2, key2, sig2, _, _ = gossip.items_of([bytes(data[int(s):int(s) + len(m)]) for s, m in zip(starts, msgs)])
+    got = engine.verify_raw(0, data2, off2, ln2, key2, sig2)
+    h = np.zeros((off2.size, 32), np.uint8)
+    for i in range(off2.size):
+        seg = np.ascontiguousarray(data2[int(off2[i]):int(off2[i]) + int(ln2[i])])
+        ref.ref_sha256d(P(seg), ctypes.c_size_t(seg.size), P(h[i]))
+    want = util.ref_verify(ref, 0, h, key2, sig2, threads=8)
+    assert np.array_equal(got, want)
+    assert 0 < (want == 0).sum() < want.size // 10
+
+
+def _dropin(engine):
+    lib = engine.lib
+    lib.check_signed_hash.restype = ctypes.c_bool
+    lib.check_signed_hash_nodeid.restype = ctypes.c_bool
+    lib.check_schnorr_sig.restype = ctypes.c_bool
+    lib.pubkey_from_der.restype = ctypes.c_bool
+    return lib
+
+
+def test_dropin_cln_signatures(engine, ref):
+    """check_signed_hash / check_signed_hash_nodeid / check_schnorr_sig / sha256_double / pubkey_from_der with
+    CLN's own argument types (opaque libsecp256k1 structs produced by the reference's parsers)."""
+    lib = _dropin(engine)
+    w = util.corrupt(util.make_signed(ref, 120, seed=99), every=4)
+    n_checked = 0
+    for i in range(120):
+        opk, osig = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        if not ref.ref_make_opaque_pubkey(P(np.ascontiguousarray(w["pub33"][i])), P(opk)):
+            out = np.zeros(64, np.uint8)
+            assert not lib.pubkey_from_der(P(np.ascontiguousarray(w["pub33"][i])), ctypes.c_size_t(33), P(out))
+            continue
+        out = np.zeros(64, np.uint8)
+        assert lib.pubkey_from_der(P(np.ascontiguousarray(w["pub33"][i])), ctypes.c_size_t(33), P(out))
+        assert np.array_equal(out, opk), "pubkey_from_der must produce the reference's opaque struct"
+        if not ref.ref_make_opaque_sig(P(np.ascontiguousarray(w["sig"][i])), P(osig)):
+            continue  # CLN refuses such a signature at wire-parse time (wire/fromwire.c:188-199)
+        h = np.ascontiguousarray(w["msg"][i])
+        want = ref.ref_check_signed_hash_opaque(P(h), P(osig), P(opk))
+        assert bool(lib.check_signed_hash(P(h), P(osig), P(opk))) == bool(want), i
+        nid = np.ascontiguousarray(w["pub33"][i])
+        assert bool(lib.check_signed_hash_nodeid(P(h), P(osig), P(nid))) == bool(want), i
+        s = np.ascontiguousarray(w["ssig"][i])
+        want_s = ref.ref_check_schnorr_sig_opaque(P(h), P(opk), P(s))
+        assert want_s >= 0
+        assert bool(lib.check_schnorr_sig(P(h), P(opk), P(s))) == bool(want_s), i
+        n_checked += 1
+    assert n_checked > 80
+    d = np.arange(200, dtype=np.uint8)
+    out, want = np.zeros(32, np.uint8), np.zeros(32, np.uint8)
+    for ln in (0, 1, 64, 174, 200):
+        lib.sha256_double(P(out), P(d), ctypes.c_size_t(ln))
+        ref.ref_sha256d(P(d), ctypes.c_size_t(ln), P(want))
+        assert np.array_equal(out, want)
+
+
+def test_dropin_gossip_batch_and_which_signature(engine, ref):
+    lib = _dropin(engine)
+    m = gossip.chan_ann_3703()
+    good = [x for x in gossip.load_subset() if x[:2] == b"\x01\x00"][:50]
+    msgs = [m, gossip.strip_features(m)] + good
+    bad = bytearray(good[3]); bad[400] ^= 1  # inside bitcoin_key_2 / signed region -> all four fail, first wins
+    msgs.append(bytes(bad))
+    bad2 = bytearray(good[4]); bad2[2 + 64 * 2 + 5] ^= 1  # corrupt bitcoin_signature_1 only
+    msgs.append(bytes(bad2))
+    arr = (ctypes.c_char_p * len(msgs))(*msgs)
+    lens = (ctypes.c_size_t * len(msgs))(*[len(x) for x in msgs])
+    st = (ctypes.c_int * len(msgs))()
+    lib.sigcheck_channel_announcement_batch(arr, lens, ctypes.c_size_t(len(msgs)), st)
+    st = list(st)
+    assert st[0] == 1, "as received: Bad node_signature_1 (run-check_channel_announcement.c:84)"
+    assert st[1] == 2, "re-encoded without features: Bad node_signature_2 (:107)"
+    assert st[2:52] == [0] * 50
+    assert st[52] == 1 and st[53] == 3
+    na = [x for x in gossip.load_subset() if x[:2] == b"\x01\x01"][:40]
+    nb = bytearray(na[5]); nb[-1] ^= 1
+    na.append(bytes(nb))
+    arr = (ctypes.c_char_p * len(na))(*na)
+    lens = (ctypes.c_size_t * len(na))(*[len(x) for x in na])
+    st = (ctypes.c_int * len(na))()
+    lib.sigcheck_node_announcement_batch(arr, lens, ctypes.c_size_t(len(na)), st)
+    assert list(st) == [0] * 40 + [1]
+
+
+def test_dropin_htlc_batch_shared_key(engine, ref):
+    """channeld's HTLC loop shape: up to 483 signatures by ONE key over distinct sighashes."""
+    lib = _dropin(engine)
+    n = 483
+    rng = np.random.default_rng(4)
+    sk = rng.integers(1, 256, size=32, dtype=np.uint8)
+    pub33, opk = np.zeros(33, np.uint8), np.zeros(64, np.uint8)
+    assert ref.ref_pubkey_create(P(sk), P(pub33), None) and ref.ref_make_opaque_pubkey(P(pub33), P(opk))
+    hashes = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sigs = np.zeros((n, 68), np.uint8)  # struct bitcoin_signature: 64-byte opaque sig + enum (4 bytes)
+    for i in range(n):
+        s64, o = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        assert ref.ref_ecdsa_sign(P(sk), P(hashes[i]), P(s64)) and ref.ref_make_opaque_sig(P(s64), P(o))
+        sigs[i, :64] = o
+        sigs[i, 64] = 1
+    hashes[17, 0] ^= 1
+    sigs[300, 10] ^= 1
+    ok = (ctypes.c_bool * n)()
+    lib.check_tx_sigs_batch(P(hashes), P(sigs), P(opk), ctypes.c_size_t(n), ok)
+    ok = np.array(list(ok))
+    assert not ok[17] and not ok[300] and ok.sum() == n - 2
+
+
+def test_full_size_properties(engine):
+    """BASELINE config C2 size (1M): generator output is all-valid; corrupting known positions flips exactly
+    those verdicts; verdicts are independent of batch position (shuffle -> same multiset, permuted)."""
+    import torch
+    n = 1_000_000
+    msg = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    key = torch.empty((n, 33), dtype=torch.uint8, device="cuda")
+    sig = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    ver = torch.empty(n, dtype=torch.uint8, device="cuda")
+    engine.synth_device(0, 77, n, msg.data_ptr(), key.data_ptr(), sig.data_ptr())
+    engine.verify_device(0, msg.data_ptr(), key.data_ptr(), sig.data_ptr(), n, ver.data_ptr())
+    engine.sync()
+    assert int(ver.sum().item()) == n
+    bad = torch.arange(3, n, 997, device="cuda")
+    msg[bad, 7] ^= 0x20
+    engine.verify_device(0, msg.data_ptr(), key.data_ptr(), sig.data_ptr(), n, ver.data_ptr())
+    engine.sync()
+    expect = torch.ones(n, dtype=torch.uint8, device="cuda")
+    expect[bad] = 0
+    assert torch.equal(ver, expect)
+    perm = torch.randperm(n, device="cuda")
+    m2, k2, s2 = msg[perm].contiguous(), key[perm].contiguous(), sig[perm].contiguous()
+    v2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    engine.verify_device(0, m2.data_ptr(), k2.data_ptr(), s2.data_ptr(), n, v2.data_ptr())
+    engine.sync()
+    assert torch.equal(v2, expect[perm])

@@ -163,8 +163,8 @@ def test_full_verify_golden_vectors(emul):
 
 
 def test_full_verify_adversarial_scalars(emul, ref):
-    msg, pub33, pubxy, sig = adversarial.cases()
-    assert msg.shape[0] > 500
+    msg, pub33, pubxy, sig = adversarial.load()
+    assert msg.shape[0] > 1000
     want = util.ref_verify(ref, 0, msg, pub33, sig)
     assert want.all(), "crafted signatures must be valid under the reference"
     assert np.array_equal(emul_verify(emul, 0, msg, pub33, sig), want)
