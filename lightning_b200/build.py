@@ -19,6 +19,8 @@ EMUL = os.path.join(ROOT, "tests", "host_emul", "libemul.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    # curve-side kernel variant: inlined field arithmetic + CTA-wide re-convergence barriers (see engine.cu)
+    "-DSV_FE_INLINE", "-DSV_MAIN_SYNC",
 ]
 
 

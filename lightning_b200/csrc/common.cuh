@@ -38,6 +38,14 @@
 #define SV_CDATA
 #endif
 
+// CTA-wide re-convergence points of the curve-side kernel (only in the SV_MAIN_SYNC build variant, where the
+// field arithmetic is inlined and the warps of a CTA are kept at the same PC to share instruction fetches)
+#if defined(__CUDACC__) && defined(SV_MAIN_SYNC)
+#define SV_SYNC() __syncthreads()
+#else
+#define SV_SYNC() ((void)0)
+#endif
+
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef uint8_t u8;

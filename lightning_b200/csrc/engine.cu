@@ -23,11 +23,24 @@
 #include "../../include/cln_sigverify.h"
 #include "verify.cuh"
 
+// Build variants of the curve-side kernel (measured on B200, 1 M ECDSA33 verifications, profiles/):
+//   default  SV_FE_INLINE + SV_MAIN_SYNC, 256 threads x 2 CTAs/SM : field arithmetic inlined, the warps of a CTA
+//            re-converge at a __syncthreads() before every point operation so that they walk the (large) code
+//            together and share instruction fetches                                    -> 43.7 M verifies/s
+//   -DSV_NO_SYNC_INLINE  fe_mul/fe_sqr as real functions, 128 x 4, no barriers        -> 39.2 M verifies/s
+//   (everything inlined WITHOUT barriers starves on instruction fetch                  -> 25.9 M verifies/s)
+#if !defined(SV_NO_SYNC_INLINE) && !defined(SV_FE_INLINE)
+#error "compile with -DSV_FE_INLINE -DSV_MAIN_SYNC (default build) or -DSV_NO_SYNC_INLINE; see lightning_b200/build.py"
+#endif
 #ifndef SV_MAIN_BLOCK
+#ifdef SV_MAIN_SYNC
+#define SV_MAIN_BLOCK 256
+#else
 #define SV_MAIN_BLOCK 128
 #endif
+#endif
 #ifndef SV_MAIN_MINB
-#define SV_MAIN_MINB 4
+#define SV_MAIN_MINB (512 / SV_MAIN_BLOCK)
 #endif
 
 // -------------------------------------------------------------------------------------------------
@@ -89,17 +102,47 @@ __global__ void __launch_bounds__(128) k_prep_schnorr(const u8* msg, const u8* k
 
 // curve side: one thread per verification, persistent grid-stride loop.  Per-thread odd-multiples
 // table lives in an HBM/L2-resident scratch slab (768 B per thread, 64-byte entries read with LDG.128).
+// record used by lanes past the end of the batch: harmless scalars (k1 = k2 = 1, u1 = 0), never valid.
+// (They must not alias a live record: the BIP-340 path overwrites records with the parked R.)
+__device__ sv_work g_idle_work = {{1, 0, 0, 0, 0}, {1, 0, 0, 0, 0}, {0}, 0, {0}};
+
 template <int KIND>
 __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
-    k_main(const sv_work* __restrict__ work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
+    k_main(sv_work* work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
            const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict) {
     const size_t keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     qtab_entry* tab = scratch + tid * 8;
-    for (size_t i = tid; i < n; i += stride) {
-        verdict[i] = (u8)verify_curve_side(KIND, work + i, key + keylen * i, sig + 64 * i, gtab, tab);
+    // CTA-uniform trip count (lanes past the end redo item 0 and discard the result) so that every thread
+    // reaches every SV_SYNC() of the barrier-synchronised build variant
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        size_t i = base + threadIdx.x;
+        bool active = i < n;
+        size_t j = active ? i : 0;
+        const sv_work* w = active ? (work + i) : &g_idle_work;
+        if (KIND == SV_KIND_SCHNORR) {
+            // park R in the work record; k_final_schnorr turns it into a verdict (batched inversion)
+            bool ok = (w->flags & SV_WF_VALID) != 0;
+            ge Q;
+            ok = key_decode(Q, KIND, key + keylen * j) && ok;
+            gej R;
+            ecmult_uniform(R, w, Q, gtab, tab);
+            if (active) schnorr_park(reinterpret_cast<sv_jac*>(work + i), R, ok);
+        } else {
+            u32 v = verify_curve_side(KIND, w, key + keylen * j, sig + 64 * j, gtab, tab);
+            if (active) verdict[i] = (u8)v;
+        }
     }
+}
+
+static_assert(sizeof(sv_jac) == sizeof(sv_work), "R is parked in place of the work record");
+__global__ void __launch_bounds__(64) k_final_schnorr(const sv_work* work, const u8* sig, size_t n, u8* verdict) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t base = t * SV_FINAL_BATCH;
+    if (base >= n) return;
+    int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
+    schnorr_final_batch(verdict + base, reinterpret_cast<const sv_jac*>(work) + base, sig + 64 * base, cnt);
 }
 
 __global__ void k_pack_bitmap(const u8* verdict, size_t n, u32* bitmap) {
@@ -555,7 +598,12 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
     else if (kind == SV_KIND_ECDSA_XY)
         k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
     else
+    {
         k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+        size_t threads = (n + SV_FINAL_BATCH - 1) / SV_FINAL_BATCH;
+        k_final_schnorr<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_work, d_sig, n, d_verdict);
+        ctx->launches += 1;
+    }
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
     ctx->launches += 2;
     if (d_bitmap) {

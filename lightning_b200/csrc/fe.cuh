@@ -266,7 +266,7 @@ SV_HD void fe_reduce512(fe& r, const u32 t[16]) {
 // for instructions (stall_no_instruction 4.5 per issue, issue slots 39 % busy): the ladder body was
 // ~44 KB of straight-line code against a 32 KB L1.5 / ~6 KB L0 instruction cache.  As functions the two
 // bodies (~4 KB together) stay L0-resident and carry ~85 % of all executed instructions.
-#if SV_DEVICE_CODE
+#if SV_DEVICE_CODE && !defined(SV_FE_INLINE)
 static __device__ __noinline__ fe fe_mul_fn(fe a, fe b) {
     u32 t[16];
     fe r;
@@ -323,6 +323,29 @@ SV_HD void fe_mul_small(fe& r, const fe& a, u32 k) {
     q = (u64)r.v[1] + c2 + (q >> 32);
     r.v[1] = (u32)q;
     r.v[2] = (u32)((u64)r.v[2] + (q >> 32));
+}
+
+// Small multiples on the ALU pipe only (the multiplier pipe is the bottleneck of the curve-side kernel):
+// 3a = a + a + a ; 8a = (a << 3) with the three bits shifted out folded back through 2^256 == 2^32 + 977.
+SV_HD void fe_mul3(fe& r, const fe& a) {
+    fe t;
+    fe_add(t, a, a);
+    fe_add(r, t, a);
+}
+SV_HD void fe_mul8(fe& r, const fe& a) {
+    u32 top = a.v[7] >> 29;  // < 8
+    u32 s[8];
+    SV_UNROLL
+    for (int i = 7; i > 0; i--) s[i] = (a.v[i] << 3) | (a.v[i - 1] >> 29);
+    s[0] = a.v[0] << 3;
+    // + top * (2^32 + 977): top*977 < 2^13
+    u32 add0 = top * SV_PC;
+    fe x, y;
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) { x.v[i] = s[i]; y.v[i] = 0; }
+    y.v[0] = add0;
+    y.v[1] = top;
+    fe_add(r, x, y);
 }
 
 SV_HD void fe_sqr_n(fe& r, const fe& a, int n) {

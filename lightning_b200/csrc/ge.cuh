@@ -42,7 +42,7 @@ SV_HD void gej_double(gej& r, const gej& a) {
     fe_sub(t, t, A);
     fe_sub(t, t, C);
     fe_dbl(D, t);
-    fe_mul_small(E, A, 3);
+    fe_mul3(E, A);
     fe_mul(t, a.y, a.z);
     fe_dbl(r.z, t);
     fe_sqr(t, E);
@@ -50,7 +50,7 @@ SV_HD void gej_double(gej& r, const gej& a) {
     fe_sub(r.x, t, D);
     fe_sub(t, D, r.x);
     fe_mul(t, t, E);
-    fe_mul_small(C, C, 8);
+    fe_mul8(C, C);
     fe_sub(r.y, t, C);
     r.inf = a.inf;
 }
@@ -118,12 +118,12 @@ SV_HD bool ge_set_xo(ge& r, const fe& x, bool odd) {
     fe_mul(c, c, x);
     fe_set_u32(seven, 7);
     fe_add(c, c, seven);
-    if (!fe_sqrt(y, c)) return false;
+    bool ok = fe_sqrt(y, c);  // no early exit: see key_decode
     fe_normalize(y);
     if (fe_is_odd(y) != odd) fe_neg(y, y);
     r.x = x;
     r.y = y;
-    return true;
+    return ok;
 }
 
 // Jacobian -> affine with a supplied 1/Z.   reference: secp256k1_ge_set_gej_zinv (group_impl.h:99)

@@ -178,25 +178,26 @@ SV_HD void sc_batch_inverse(sc* v, int n) {
 
 // decode the public key of item `kind`; false -> verdict 0
 SV_HD bool key_decode(ge& Q, int kind, const u8* key) {
+    // No early exits: every lane runs the same instruction stream (an invalid key just carries a false
+    // flag and garbage coordinates through the ladder), so CTA-wide barriers stay legal and nothing is
+    // lost — in SIMT a lane that leaves early saves no time while its warp keeps going.
     if (kind == SV_KIND_ECDSA33) {
         // eckey_impl.h:17-20: prefix must be 02/03, x < p, x^3+7 a residue
         u8 pfx = key[0];
         fe x;
         bool ok = (pfx == 2 || pfx == 3);
         ok = fe_set_b32(x, key + 1) && ok;
-        if (!ok) return false;
-        return ge_set_xo(Q, x, pfx == 3);
+        return ge_set_xo(Q, x, pfx == 3) && ok;
     } else if (kind == SV_KIND_ECDSA_XY) {
         // eckey_impl.h:21-33 (65-byte form without the 04 prefix): x,y < p and on the curve
         bool ok = fe_set_b32(Q.x, key);
         ok = fe_set_b32(Q.y, key + 32) && ok;
-        if (!ok) return false;
-        return ge_is_on_curve(Q);
+        return ge_is_on_curve(Q) && ok;
     } else {
         // extrakeys/main_impl.h:32-38: x < p, lift to the even-y point
         fe x;
-        if (!fe_set_b32(x, key)) return false;
-        return ge_set_xo(Q, x, false);
+        bool ok = fe_set_b32(x, key);
+        return ge_set_xo(Q, x, false) && ok;
     }
 }
 
@@ -231,6 +232,7 @@ SV_HD void qtable_build(qtab_entry* tab, fe& zc, const ge& Q) {
 #endif
     for (int k = 1; k < 8; k++) {
         fe h;
+        SV_SYNC();
         gej_add_ge(acc, acc, d_aff, &h);  // (2k+1)Q ; never exceptional for a point of prime order > 15
         fe_to_words(tab[k].x, acc.x);
         fe_to_words(tab[k].y, acc.y);
@@ -258,20 +260,27 @@ SV_HD void qtable_build(qtab_entry* tab, fe& zc, const ge& Q) {
             fe_mul(zr, zr, t);
         }
     }
+    // the ratio slots are free now: store beta*x there, the x coordinate of lambda*P (endomorphism half)
+    fe beta;
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) beta.v[i] = GE_BETA[i];
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int k = 0; k < 8; k++) {
+        fe t;
+        fe_from_words(t, tab[k].x);
+        fe_mul(t, t, beta);
+        fe_to_words(tab[k].h, t);
+    }
 }
 
 // fetch table entry for window value v (0..15) of a scalar with sign `sneg`; lam -> apply beta
 SV_HD void qtable_fetch(ge& p, const qtab_entry* tab, u32 v, u32 sneg, bool lam) {
     u32 dneg = (v < 8) ? 1u : 0u;
     u32 idx = dneg ? (7u - v) : (v - 8u);
-    fe_from_words(p.x, tab[idx].x);
+    fe_from_words(p.x, lam ? tab[idx].h : tab[idx].x);  // h slot holds beta*x
     fe_from_words(p.y, tab[idx].y);
-    if (lam) {
-        fe beta;
-        SV_UNROLL
-        for (int i = 0; i < 8; i++) beta.v[i] = GE_BETA[i];
-        fe_mul(p.x, p.x, beta);
-    }
     if (dneg ^ sneg) fe_neg(p.y, p.y);
 }
 
@@ -299,12 +308,16 @@ SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* g
 #if SV_DEVICE_CODE
 #pragma unroll 1
 #endif
-        for (int j = 0; j < 4; j++) gej_double(R, R);
+        for (int j = 0; j < 4; j++) {
+            SV_SYNC();
+            gej_double(R, R);
+        }
 #if SV_DEVICE_CODE
 #pragma unroll 1
 #endif
         for (int half = 0; half < 2; half++) {
             u32 v = half ? window4(m2, i) : window4(m1, i);
+            SV_SYNC();
             qtable_fetch(p, tab, v, half ? s2 : s1, half != 0);
             gej_add_ge(R, R, p);
         }
@@ -317,6 +330,7 @@ SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* g
 #endif
     for (int row = 0; row < 16; row++) {
         int d = w->gd[row];
+        SV_SYNC();
         if (d != 0) {
             u32 a = (u32)(d < 0 ? -d : d);
             ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
@@ -359,16 +373,71 @@ SV_HD u32 schnorr_final(const gej& R, const u8* sig64) {
     return fe_equal(rx, a.x) ? 1u : 0u;
 }
 
+// BIP-340 needs the affine R (y parity): one field inversion per signature.  Instead of inverting inside the
+// ladder kernel, it parks R = (X,Y,Z) in the (now dead) 128-byte work record and a small second kernel inverts
+// 16 Z's at a time with Montgomery's trick (3 mults per signature + 1/16 of a Fermat exponentiation).
+struct alignas(16) sv_jac {
+    u32 x[8], y[8], z[8];
+    u32 inf, ok, pad[6];
+};
+#define SV_FINAL_BATCH 16
+
+SV_HD void schnorr_park(sv_jac* out, const gej& R, bool ok) {
+    fe_to_words(out->x, R.x);
+    fe_to_words(out->y, R.y);
+    fe_to_words(out->z, R.z);
+    out->inf = R.inf;
+    out->ok = ok ? 1u : 0u;
+}
+
+// verdicts for cnt (<= SV_FINAL_BATCH) consecutive parked results
+SV_HD void schnorr_final_batch(u8* verdict, const sv_jac* jac, const u8* sig64, int cnt) {
+    fe pre[SV_FINAL_BATCH];
+    fe acc, one;
+    fe_set_u32(one, 1);
+    for (int i = 0; i < cnt; i++) {
+        fe z;
+        fe_from_words(z, jac[i].z);
+        bool usable = jac[i].ok && !jac[i].inf && !fe_is_zero(z);
+        if (!usable) z = one;
+        if (i == 0) pre[0] = z; else fe_mul(pre[i], pre[i - 1], z);
+    }
+    fe_inv(acc, pre[cnt - 1]);
+    for (int i = cnt - 1; i >= 0; i--) {
+        fe z, zi;
+        fe_from_words(z, jac[i].z);
+        bool usable = jac[i].ok && !jac[i].inf && !fe_is_zero(z);
+        if (!usable) z = one;
+        if (i > 0) {
+            fe_mul(zi, acc, pre[i - 1]);
+            fe_mul(acc, acc, z);
+        } else {
+            zi = acc;
+        }
+        gej R;
+        fe_from_words(R.x, jac[i].x);
+        fe_from_words(R.y, jac[i].y);
+        ge a;
+        ge_set_gej_zinv(a, R, zi);
+        fe_normalize(a.y);
+        fe rx;
+        fe_set_b32(rx, sig64 + 64 * i);
+        bool good = usable && !fe_is_odd(a.y) && fe_equal(rx, a.x);  // main_impl.h:255-264
+        verdict[i] = good ? 1 : 0;
+    }
+}
+
 // whole curve side for one item
 SV_HD u32 verify_curve_side(int kind, const sv_work* w, const u8* key, const u8* sig64, const ge_mem* gtab,
                             qtab_entry* tab) {
     u32 flags = w->flags;
-    if (!(flags & SV_WF_VALID)) return 0;
+    bool ok = (flags & SV_WF_VALID) != 0;  // an invalid record carries harmless dummy scalars (k1 = k2 = 1, u1 = 0)
     ge Q;
-    if (!key_decode(Q, kind, key)) return 0;
+    ok = key_decode(Q, kind, key) && ok;
     gej R;
     ecmult_uniform(R, w, Q, gtab, tab);
-    return (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);
+    u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);
+    return ok ? v : 0u;
 }
 
 // =================================================================================================

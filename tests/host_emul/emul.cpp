@@ -71,6 +71,8 @@ void emul_fe_op(int op, const u32* a, const u32* b, u32* out) {
         case 5: { bool ok = fe_sqrt(r, x); if (!ok) fe_set_zero(r); break; }
         case 6: fe_neg(r, x); break;
         case 7: fe_mul_small(r, x, y.v[0]); break;
+        case 8: fe_mul3(r, x); break;
+        case 9: fe_mul8(r, x); break;
         default: fe_set_zero(r);
     }
     fe_normalize(r);
@@ -164,6 +166,21 @@ void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, si
         }
     }
     qtab_entry tab[8];
+    if (kind == SV_KIND_SCHNORR) {  // as k_main<SCHNORR> + k_final_schnorr: park R, then batched inversion
+        for (size_t i = 0; i < n; i++) {
+            bool ok = (work[i].flags & SV_WF_VALID) != 0;
+            ge Q;
+            ok = key_decode(Q, kind, key + keylen * i) && ok;
+            gej R;
+            ecmult_uniform(R, &work[i], Q, g_table.data(), tab);
+            schnorr_park(reinterpret_cast<sv_jac*>(&work[i]), R, ok);
+        }
+        for (size_t base = 0; base < n; base += SV_FINAL_BATCH) {
+            int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
+            schnorr_final_batch(out + base, reinterpret_cast<const sv_jac*>(work.data()) + base, sig + 64 * base, cnt);
+        }
+        return;
+    }
     for (size_t i = 0; i < n; i++)
         out[i] = (u8)verify_curve_side(kind, &work[i], key + keylen * i, sig + 64 * i, g_table.data(), tab);
 }

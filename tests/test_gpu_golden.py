@@ -56,29 +56,23 @@ def test_adversarial_scalars(engine, ref):
 
 def test_gossip_replay_device_hashing(engine, ref):
     """config C4 in miniature: the mainnet gossip fixture tiled x7, device-side SHA-256d of msg[258:] / msg[66:],
-    ~1 % of messages bit-flipped; every verdict diffed against the reference run on the same bytes."""
-    msgs = gossip.load_subset() * 7
-    data, off, ln, key, sig, owner, which = gossip.items_of(msgs)
+    ~1 % of messages bit-flipped (signatures, keys or signed bytes; never the type/length fields, which CLN's
+    wire parser would reject before any signature check); every verdict diffed against the reference."""
+    msgs = [bytearray(m) for m in gossip.load_subset() * 7]
     rng = np.random.default_rng(1)
-    flip = rng.choice(len(msgs), size=len(msgs) // 100, replace=False)
-    starts = np.cumsum([0] + [len(m) for m in msgs])[:-1]
-    for mi in flip:
-        pos = int(starts[mi]) + int(rng.integers(2, len(msgs[mi])))
-        data[pos] ^= 1 << int(rng.integers(0, 8))
+    for mi in rng.choice(len(msgs), size=len(msgs) // 100, replace=False):
+        while True:
+            pos = int(rng.integers(2, len(msgs[mi])))
+            if pos not in (66, 67, 258, 259):
+                break
+        msgs[mi][pos] ^= 1 << int(rng.integers(0, 8))
+    data, off, ln, key, sig, owner, which = gossip.items_of([bytes(m) for m in msgs])
     got = engine.verify_raw(0, data, off, ln, key, sig)
-    # reference: hash each span with CCAN sha256 (sha256_double), then parse + verify
-    h = np.zeros((off.size, 32), np.uint8)
+    h = np.zeros((off.size, 32), np.uint8)  # reference: CCAN sha256 twice (sha256_double), then parse + verify
     for i in range(off.size):
         seg = np.ascontiguousarray(data[int(off[i]):int(off[i]) + int(ln[i])])
         ref.ref_sha256d(P(seg), ctypes.c_size_t(seg.size), P(h[i]))
-    # sigs/keys may have been hit by the flips too: re-slice them from the mutated bytes
-    data2, off2, ln2, key2, sig2, _, _ = gossip.items_of([bytes(data[int(s):int(s) + len(m)]) for s, m in zip(starts, msgs)])
-    got = engine.verify_raw(0, data2, off2, ln2, key2, sig2)
-    h = np.zeros((off2.size, 32), np.uint8)
-    for i in range(off2.size):
-        seg = np.ascontiguousarray(data2[int(off2[i]):int(off2[i]) + int(ln2[i])])
-        ref.ref_sha256d(P(seg), ctypes.c_size_t(seg.size), P(h[i]))
-    want = util.ref_verify(ref, 0, h, key2, sig2, threads=8)
+    want = util.ref_verify(ref, 0, h, key, sig, threads=8)
     assert np.array_equal(got, want)
     assert 0 < (want == 0).sum() < want.size // 10
 
@@ -194,6 +188,7 @@ def test_full_size_properties(engine):
     assert int(ver.sum().item()) == n
     bad = torch.arange(3, n, 997, device="cuda")
     msg[bad, 7] ^= 0x20
+    torch.cuda.synchronize()  # torch's stream produced the inputs; the engine runs on its own stream
     engine.verify_device(0, msg.data_ptr(), key.data_ptr(), sig.data_ptr(), n, ver.data_ptr())
     engine.sync()
     expect = torch.ones(n, dtype=torch.uint8, device="cuda")
@@ -202,6 +197,7 @@ def test_full_size_properties(engine):
     perm = torch.randperm(n, device="cuda")
     m2, k2, s2 = msg[perm].contiguous(), key[perm].contiguous(), sig[perm].contiguous()
     v2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     engine.verify_device(0, m2.data_ptr(), k2.data_ptr(), s2.data_ptr(), n, v2.data_ptr())
     engine.sync()
     assert torch.equal(v2, expect[perm])

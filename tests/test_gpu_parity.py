@@ -41,10 +41,17 @@ def test_schnorr_random_and_corrupted(engine, ref, workload):
 
 
 def test_ragged_sizes(engine, ref, workload):
-    for n in (0, 1, 2, 15, 16, 17, 31, 33, 127, 129, 1000):
-        got = engine.verify(K33, workload["msg"][:n], workload["pub33"][:n], workload["sig"][:n])
-        want = util.ref_verify(ref, K33, workload["msg"][:n], workload["pub33"][:n], workload["sig"][:n]) if n else np.zeros(0, np.uint8)
-        assert np.array_equal(got, want), n
+    """batch sizes around the prep batch (16), the warp (32) and the CTA (128/256/512), every kind; lanes past
+    the end of a batch must not disturb live records (regression: idle lanes once aliased record 0, which the
+    BIP-340 path overwrites with the parked R)."""
+    for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ssig")]):
+        for n in (0, 1, 2, 15, 16, 17, 31, 33, 127, 129, 255, 257, 511, 513, 1000):
+            for rep in range(3 if n < 40 else 1):
+                o = rep * 40
+                m, kk, ss = workload["msg"][o:o + n], workload[k][o:o + n], workload[s][o:o + n]
+                got = engine.verify(kind, m, kk, ss)
+                want = util.ref_verify(ref, kind, m, kk, ss) if n else np.zeros(0, np.uint8)
+                assert np.array_equal(got, want), (kind, n, rep)
 
 
 def test_sha256d_spans(engine, ref):
@@ -117,6 +124,7 @@ def test_synth_generator_is_valid_under_reference(engine, ref):
         sig = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
         ver = torch.empty(n, dtype=torch.uint8, device="cuda")
         bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
         engine.synth_device(kind, 1234 + kind, n, msg.data_ptr(), key.data_ptr(), sig.data_ptr())
         engine.verify_device(kind, msg.data_ptr(), key.data_ptr(), sig.data_ptr(), n, ver.data_ptr(), bits.data_ptr())
         engine.sync()

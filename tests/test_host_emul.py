@@ -58,6 +58,7 @@ def test_field_ops_vs_python(emul):
         assert feop(emul, 6, a) == (-a) % p
         for k in (2, 3, 8, 65535):
             assert feop(emul, 7, a, k) == k * a % p
+        assert feop(emul, 8, a) == 3 * a % p and feop(emul, 9, a) == 8 * a % p
     for a in vals[:50]:
         assert feop(emul, 4, a) == pow(a, p - 2, p)
         s = feop(emul, 5, a)

@@ -1,0 +1,21 @@
+"""Small end-to-end run of every kernel, meant to be executed under compute-sanitizer."""
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import lightning_b200 as L
+from tests import util
+ref = util.load_ref()
+eng = L.SigVerifier(0)
+w = util.corrupt(util.make_signed(ref, 300, seed=3), every=5)
+for n in (1, 5, 300):
+    for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ssig")]):
+        got = eng.verify(kind, w["msg"][:n], w[k][:n], w[s][:n])
+        want = util.ref_verify(ref, kind, w["msg"][:n], w[k][:n], w[s][:n])
+        assert np.array_equal(got, want), (n, kind)
+print("batch ok")
+lib = eng.lib
+lib.check_schnorr_sig.restype = ctypes.c_bool
+opk = np.zeros(64, np.uint8)
+assert ref.ref_make_opaque_pubkey(util.P(np.ascontiguousarray(w["pub33"][1])), util.P(opk))
+r = lib.check_schnorr_sig(util.P(np.ascontiguousarray(w["msg"][1])), util.P(opk), util.P(np.ascontiguousarray(w["ssig"][1])))
+print("dropin schnorr", r)
