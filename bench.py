@@ -202,6 +202,9 @@ def run_engine(args):
     rank = env_int("RANK", 0)
     local = env_int("LOCAL_RANK", 0)
     dist = None
+    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
