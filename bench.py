@@ -52,6 +52,7 @@ def env_int(name, default):
 # clocks sampling (nvidia-smi, during the timed region)
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """One streaming `nvidia-smi -lms 100` process for the duration of the timed regions."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -59,38 +60,44 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.samples = []
-        self._stop = threading.Event()
+        self._proc = None
         self._th = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 8:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self._proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
+            if len(parts) >= 8:
+                self.samples.append(parts)
 
     def start(self):
-        self._th = threading.Thread(target=self._run, daemon=True)
-        self._th.start()
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS,
+                                           "--format=csv,noheader,nounits", "-lms", "100"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+        except Exception:
+            self._proc = None
 
     def stop(self):
-        self._stop.set()
+        if self._proc:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
         if self._th:
-            self._th.join(timeout=6)
+            self._th.join(timeout=5)
         sm = sorted(int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit())
         mx = [int(float(s[2])) for s in self.samples if s[2].replace(".", "").isdigit()]
+        pw = [float(s[3]) for s in self.samples if s[3].replace(".", "").isdigit()]
         reasons = set()
         for s in self.samples:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -263,7 +270,6 @@ def run_engine(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = eng.info()["launches"] - launches0
     # per-kernel device time (events recorded by the engine on the launch stream), a few extra steps
     for i in range(3):
@@ -312,6 +318,7 @@ def run_engine(args):
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t_e.item())
+    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions
     e2e_matches = bool(np.array_equal(np.asarray(h_out), (torch.ones(n, dtype=torch.uint8).index_fill_(0, batches[0][3].cpu(), 0)).numpy()))
 
     if rank != 0:
@@ -336,6 +343,8 @@ def run_engine(args):
     # ---- CPU baseline on a bounded sample of THIS workload, verdicts compared bit for bit ----
     cpu = None
     try:
+        if world > 1:
+            raise RuntimeError("reported at N=1 only")
         lib, ckind = load_ref()
         threads = host_threads()
         m = int(min(n, max(20_000, 30_000 * threads)))

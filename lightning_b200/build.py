@@ -73,7 +73,8 @@ def build_host_emul(force=False):
 
 
 def build_oracle():
-    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], capture_output=True, text=True,
+                       stdin=subprocess.DEVNULL, timeout=900)
     if r.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
 

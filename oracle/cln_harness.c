@@ -1,0 +1,173 @@
+/*
+ * oracle/cln_harness.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * BASELINE config C1 ("reference plumbing"): CLN's own, UNMODIFIED bitcoin/signature.c, bitcoin/pubkey.c,
+ * bitcoin/shadouble.c, common/node_id.c, gossipd/sigcheck.c and wire/fromwire.c are compiled where they
+ * lie under /root/reference (recipe: SURVEY.md §8(c)3+4, oracle/Makefile target `cln`) on top of the
+ * libwally+libsecp256k1 amalgamation.  This file supplies (a) the handful of externs that normally come
+ * from common/utils.c (which needs libsodium) — the same trick the reference's unit tests use with their
+ * auto-generated stubs — and (b) flat C entry points for ctypes.  Output: oracle/_ref/libcln_ref.so.
+ */
+#include "config.h"
+#include <bitcoin/pubkey.h>
+#include <bitcoin/shadouble.h>
+#include <bitcoin/signature.h>
+#include <ccan/tal/str/str.h>
+#include <common/amount.h>
+#include <common/node_id.h>
+#include <gossipd/sigcheck.h>
+#include <secp256k1.h>
+#include <stdlib.h>
+#include <string.h>
+#include <wire/wire.h>
+
+/* ---- what common/utils.c / common/setup.c would provide ---- */
+secp256k1_context *secp256k1_ctx;
+const tal_t *tmpctx;
+const tal_t *wally_tal_ctx;
+const struct chainparams *chainparams;
+bool is_elements(const struct chainparams *cp) { (void)cp; return false; }
+void tal_wally_start(void) {}
+void tal_wally_end(const tal_t *parent) { (void)parent; }
+struct amount_sat psbt_input_get_amount(const struct wally_psbt *psbt, size_t in) { (void)psbt; (void)in; abort(); }
+bool utf8_check(const void *buf, size_t len) { (void)buf; (void)len; return true; }
+char *tal_hexstr(const tal_t *ctx, const void *data, size_t len) {
+    static const char d[] = "0123456789abcdef";
+    char *s = tal_arr(ctx, char, len * 2 + 1);
+    for (size_t i = 0; i < len; i++) { s[2 * i] = d[((const u8 *)data)[i] >> 4]; s[2 * i + 1] = d[((const u8 *)data)[i] & 15]; }
+    s[2 * len] = 0;
+    return s;
+}
+char *tal_hex(const tal_t *ctx, const tal_t *data) { return tal_hexstr(ctx, data, tal_bytelen(data)); }
+
+static void setup(void) {
+    if (secp256k1_ctx) return;
+    secp256k1_ctx = secp256k1_context_create(SECP256K1_CONTEXT_VERIFY | SECP256K1_CONTEXT_SIGN); /* common/setup.c:58 */
+    tmpctx = tal(NULL, char);
+}
+static void sweep(void) { tal_free(tmpctx); tmpctx = tal(NULL, char); }
+
+/* parse exactly as CLN's wire layer does (wire/fromwire.c:188-199, bitcoin/pubkey.c:14,102), then call the
+ * reference entry point.  Returns 1/0 = verdict, -1 = the wire layer refuses the encoding. */
+int cln_check_signed_hash(const u8 *hash32, const u8 *sig64, const u8 *pub33) {
+    setup();
+    secp256k1_ecdsa_signature sig;
+    struct pubkey key;
+    struct sha256_double h;
+    const u8 *p = sig64;
+    size_t max = 64;
+    fromwire_secp256k1_ecdsa_signature(&p, &max, &sig);
+    if (!p) return -1;
+    if (!pubkey_from_der(pub33, 33, &key)) return -1;
+    memcpy(h.sha.u.u8, hash32, 32);
+    return check_signed_hash(&h, &sig, &key);
+}
+int cln_check_signed_hash_nodeid(const u8 *hash32, const u8 *sig64, const u8 *node_id33) {
+    setup();
+    secp256k1_ecdsa_signature sig;
+    struct node_id id;
+    struct sha256_double h;
+    const u8 *p = sig64;
+    size_t max = 64;
+    fromwire_secp256k1_ecdsa_signature(&p, &max, &sig);
+    if (!p) return -1;
+    memcpy(id.k, node_id33, 33);
+    memcpy(h.sha.u.u8, hash32, 32);
+    return check_signed_hash_nodeid(&h, &sig, &id);
+}
+int cln_check_schnorr_sig(const u8 *hash32, const u8 *pub33, const u8 *sig64) {
+    setup();
+    struct pubkey key;
+    struct sha256 h;
+    struct bip340sig s;
+    if (!pubkey_from_der(pub33, 33, &key)) return -1;
+    memcpy(h.u.u8, hash32, 32);
+    memcpy(s.u8, sig64, 64);
+    return check_schnorr_sig(&h, &key.pubkey, &s);
+}
+void cln_sha256_double(const u8 *p, size_t len, u8 *out32) {
+    struct sha256_double h;
+    sha256_double(&h, p, len);
+    memcpy(out32, h.sha.u.u8, 32);
+}
+/* opaque structs as CLN's parsers build them (for driving the engine's drop-in entry points) */
+int cln_make_opaque(const u8 *sig64, const u8 *pub33, u8 *sig_opaque64, u8 *pub_opaque64) {
+    setup();
+    secp256k1_ecdsa_signature sig;
+    struct pubkey key;
+    const u8 *p = sig64;
+    size_t max = 64;
+    fromwire_secp256k1_ecdsa_signature(&p, &max, &sig);
+    if (!p || !pubkey_from_der(pub33, 33, &key)) return 0;
+    memcpy(sig_opaque64, sig.data, 64);
+    memcpy(pub_opaque64, key.pubkey.data, 64);
+    return 1;
+}
+
+static int which(const char *err) {
+    if (!err) return 0;
+    if (strstr(err, "node_signature_1")) return 1;
+    if (strstr(err, "node_signature_2")) return 2;
+    if (strstr(err, "bitcoin_signature_1")) return 3;
+    if (strstr(err, "bitcoin_signature_2")) return 4;
+    return 1;
+}
+/* gossipd/sigcheck.c:45-115 on a raw channel_announcement: 0 ok, 1..4 first bad signature, -1 malformed.
+ * Field offsets per wire/peer_wire.csv:340-352 (the generated fromwire_channel_announcement is not in the tree). */
+int cln_sigcheck_channel_announcement(const u8 *msg, size_t len) {
+    setup();
+    if (len < 260) return -1;
+    size_t flen = ((size_t)msg[258] << 8) | msg[259], keys = 260 + flen + 32 + 8;
+    if (len < keys + 4 * 33) return -1;
+    secp256k1_ecdsa_signature sig[4];
+    for (int k = 0; k < 4; k++) {
+        const u8 *p = msg + 2 + 64 * k;
+        size_t max = 64;
+        fromwire_secp256k1_ecdsa_signature(&p, &max, &sig[k]);
+        if (!p) return -1;
+    }
+    struct node_id id1, id2;
+    struct pubkey b1, b2;
+    memcpy(id1.k, msg + keys, 33);
+    memcpy(id2.k, msg + keys + 33, 33);
+    if (!pubkey_from_der(msg + keys + 66, 33, &b1) || !pubkey_from_der(msg + keys + 99, 33, &b2)) return -1;
+    u8 *ann = tal_dup_arr(tmpctx, u8, msg, len, 0);
+    const char *err = sigcheck_channel_announcement(tmpctx, &id1, &id2, &b1, &b2, &sig[0], &sig[1], &sig[2], &sig[3], ann);
+    int r = which(err);
+    sweep();
+    return r;
+}
+int cln_sigcheck_node_announcement(const u8 *msg, size_t len) {
+    setup();
+    if (len < 68) return -1;
+    size_t flen = ((size_t)msg[66] << 8) | msg[67], idoff = 68 + flen + 4;
+    if (len < idoff + 33) return -1;
+    secp256k1_ecdsa_signature sig;
+    const u8 *p = msg + 2;
+    size_t max = 64;
+    fromwire_secp256k1_ecdsa_signature(&p, &max, &sig);
+    if (!p) return -1;
+    struct node_id id;
+    memcpy(id.k, msg + idoff, 33);
+    u8 *ann = tal_dup_arr(tmpctx, u8, msg, len, 0);
+    const char *err = sigcheck_node_announcement(tmpctx, &id, &sig, ann);
+    int r = err ? 1 : 0;
+    sweep();
+    return r;
+}
+int cln_sigcheck_channel_update(const u8 *msg, size_t len, const u8 *node_id33) {
+    setup();
+    if (len < 66 + 32 + 8) return -1;
+    secp256k1_ecdsa_signature sig;
+    const u8 *p = msg + 2;
+    size_t max = 64;
+    fromwire_secp256k1_ecdsa_signature(&p, &max, &sig);
+    if (!p) return -1;
+    struct node_id id;
+    memcpy(id.k, node_id33, 33);
+    u8 *upd = tal_dup_arr(tmpctx, u8, msg, len, 0);
+    const char *err = sigcheck_channel_update(tmpctx, &id, &sig, upd);
+    int r = err ? 1 : 0;
+    sweep();
+    return r;
+}

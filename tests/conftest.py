@@ -20,6 +20,13 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def cln():
+    """CLN's own plumbing (bitcoin/signature.c, common/node_id.c, gossipd/sigcheck.c), unmodified."""
+    from tests import util
+    return util.load_cln()
+
+
+@pytest.fixture(scope="session")
 def emul():
     from tests import util
     return util.load_emul()

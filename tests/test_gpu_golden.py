@@ -201,3 +201,37 @@ def test_full_size_properties(engine):
     engine.verify_device(0, m2.data_ptr(), k2.data_ptr(), s2.data_ptr(), n, v2.data_ptr())
     engine.sync()
     assert torch.equal(v2, expect[perm])
+
+
+def test_config_c1_dropin_vs_cln_own_functions(engine, ref, cln):
+    """Config C1 on the GPU: the same 1k triples through the engine's drop-in check_signed_hash /
+    check_signed_hash_nodeid / check_schnorr_sig (CLN argument types, opaque structs built by CLN's own wire
+    parsers) must agree call by call with CLN's unmodified functions."""
+    lib = _dropin(engine)
+    w = util.corrupt(util.make_signed(ref, 1000, seed=20260922), every=10)
+    agree = 0
+    for i in range(1000):
+        m, k, s, ss = (np.ascontiguousarray(w[x][i]) for x in ("msg", "pub33", "sig", "ssig"))
+        want = cln.cln_check_signed_hash(P(m), P(s), P(k))
+        want_id = cln.cln_check_signed_hash_nodeid(P(m), P(s), P(k))
+        osig, opk = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        if cln.cln_make_opaque(P(s), P(k), P(osig), P(opk)):
+            assert int(lib.check_signed_hash(P(m), P(osig), P(opk))) == want, i
+            assert int(lib.check_schnorr_sig(P(m), P(opk), P(ss))) == cln.cln_check_schnorr_sig(P(m), P(k), P(ss)), i
+            agree += 1
+        osig2 = np.zeros(64, np.uint8)
+        if want_id >= 0 and ref.ref_make_opaque_sig(P(s), P(osig2)):
+            assert int(lib.check_signed_hash_nodeid(P(m), P(osig2), P(k))) == want_id, i
+    assert agree > 900
+    # batch forms vs gossipd/sigcheck.c
+    msgs = [x for x in gossip.load_subset() if x[:2] == b"\x01\x00"][:200]
+    bad = [bytearray(x) for x in msgs[:40]]
+    for j, b in enumerate(bad):
+        b[2 + 64 * (j % 4) + 7] ^= 1
+    allm = msgs + [bytes(b) for b in bad]
+    arr = (ctypes.c_char_p * len(allm))(*allm)
+    lens = (ctypes.c_size_t * len(allm))(*[len(x) for x in allm])
+    st = (ctypes.c_int * len(allm))()
+    lib.sigcheck_channel_announcement_batch(arr, lens, ctypes.c_size_t(len(allm)), st)
+    want = [cln.cln_sigcheck_channel_announcement(x, ctypes.c_size_t(len(x))) for x in allm]
+    assert list(st) == want

@@ -19,15 +19,26 @@ def load_ref():
     path = os.path.join(ROOT, "oracle", "_ref", "libsecp_ref.so")
     if not os.path.exists(path):
         if os.path.isdir("/root/reference"):
-            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdin=subprocess.DEVNULL)
         else:
             raise RuntimeError("oracle/_ref/libsecp_ref.so missing and /root/reference absent")
     return ctypes.CDLL(path)
 
 
+def load_cln():
+    """CLN's own unmodified bitcoin/signature.c + gossipd/sigcheck.c over the libwally amalgamation (config C1)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libcln_ref.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "cln"], stdin=subprocess.DEVNULL)
+        else:
+            raise RuntimeError("oracle/_ref/libcln_ref.so missing and /root/reference absent")
+    return ctypes.CDLL(path)
+
+
 def load_port():
     path = os.path.join(ROOT, "oracle", "libsecp_port.so")
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], stdin=subprocess.DEVNULL)
     return ctypes.CDLL(path)
 
 
