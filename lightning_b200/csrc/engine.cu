@@ -440,6 +440,8 @@ struct sv_ctx {
     int device;
     int sm_count;
     cudaStream_t stream;
+    cudaStream_t copy_stream;  // H2D of the next slice overlaps the kernels of the current one (sv_verify_host)
+    cudaEvent_t h2d_ev[8];
     ge_mem* d_gtab;
     ge_mem* d_bases;
     qtab_entry* d_scratch;
@@ -522,6 +524,8 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     ctx->launches = 0;
     ctx->profiling = 0;
     ctx->ev[0] = ctx->ev[1] = ctx->ev[2] = nullptr;
+    ctx->stream = ctx->copy_stream = nullptr;
+    for (int i = 0; i < 8; i++) ctx->h2d_ev[i] = nullptr;
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { int rc = fail(nullptr, SV_ERR_CUDA, "cudaGetDeviceProperties", e); delete ctx; return rc; }
@@ -530,6 +534,8 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     do {
 #define CK2(call) { cudaError_t e2 = (call); if (e2 != cudaSuccess) { rc = fail(nullptr, e2 == cudaErrorMemoryAllocation ? SV_ERR_NOMEM : SV_ERR_CUDA, #call, e2); break; } }
         CK2(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK2(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) CK2(cudaEventCreateWithFlags(&ctx->h2d_ev[i], cudaEventDisableTiming));
         CK2(cudaMalloc(&ctx->d_gtab, (size_t)SV_GT_ENTRIES * sizeof(ge_mem)));
         CK2(cudaMalloc(&ctx->d_bases, 16 * sizeof(ge_mem)));
         CK2(cudaMalloc(&ctx->d_sink, 64));
@@ -558,6 +564,8 @@ extern "C" void sv_destroy(sv_ctx* ctx) {
     cudaFree(ctx->d_msg); cudaFree(ctx->d_key); cudaFree(ctx->d_sig); cudaFree(ctx->d_verdict);
     cudaFree(ctx->d_work); cudaFree(ctx->d_data); cudaFree(ctx->d_off); cudaFree(ctx->d_len);
     for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; i++) if (ctx->h2d_ev[i]) cudaEventDestroy(ctx->h2d_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -661,14 +669,36 @@ extern "C" int sv_verify_host(sv_ctx* ctx, int kind, const uint8_t* msg32, const
     size_t chunk = n < SV_HOST_CHUNK ? n : SV_HOST_CHUNK;
     int rc = ensure_staging(ctx, chunk);
     if (rc) return rc;
+    rc = ensure_work(ctx, chunk);
+    if (rc) return rc;
+    // Software pipeline inside a chunk: slices sized in whole waves of the persistent grid; slice k+1 is copied on
+    // the copy stream while slice k runs on the compute stream.  First slice small so the kernels start early.
+    const size_t wave = (size_t)ctx->main_grid * SV_MAIN_BLOCK;
     for (size_t off = 0; off < n; off += chunk) {
         size_t c = (n - off < chunk) ? (n - off) : chunk;
-        CK(cudaMemcpyAsync(ctx->d_msg, msg32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_key, key + ks * off, ks * c, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_sig, sig64 + 64 * off, 64 * c, cudaMemcpyHostToDevice, ctx->stream));
-        rc = launch_verify(ctx, kind, ctx->d_msg, ctx->d_key, ctx->d_sig, c, ctx->d_verdict, nullptr, ctx->stream);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(verdicts + off, ctx->d_verdict, c, cudaMemcpyDeviceToHost, ctx->stream));
+        size_t done = 0;
+        int k = 0;
+        while (done < c) {
+            size_t want = (k == 0) ? 2 * wave : 8 * wave;
+            size_t s = (c - done < want + wave) ? (c - done) : want;  // do not leave a sliver behind
+            if (k >= 7) s = c - done;
+            cudaStream_t cs = (c > 2 * wave) ? ctx->copy_stream : ctx->stream;
+            CK(cudaMemcpyAsync(ctx->d_msg + 32 * done, msg32 + 32 * (off + done), 32 * s, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(ctx->d_key + ks * done, key + ks * (off + done), ks * s, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(ctx->d_sig + 64 * done, sig64 + 64 * (off + done), 64 * s, cudaMemcpyHostToDevice, cs));
+            if (cs != ctx->stream) {
+                CK(cudaEventRecord(ctx->h2d_ev[k], cs));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_ev[k], 0));
+            }
+            rc = launch_verify(ctx, kind, ctx->d_msg + 32 * done, ctx->d_key + ks * done, ctx->d_sig + 64 * done, s,
+                               ctx->d_verdict + done, nullptr, ctx->stream);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(verdicts + off + done, ctx->d_verdict + done, s, cudaMemcpyDeviceToHost, ctx->stream));
+            done += s;
+            k++;
+        }
+        // the next chunk reuses the staging buffers: its copies must not overtake this chunk's kernels
+        if (off + c < n) CK(cudaStreamSynchronize(ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return SV_OK;
