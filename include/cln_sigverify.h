@@ -80,6 +80,17 @@ int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_l
                        const uint32_t *len, const uint8_t *key, const uint8_t *sig64, size_t n,
                        uint8_t *verdicts);
 
+/* ---- gossip ingest with DEVICE-side slicing (replaces the per-message work of
+ *      gossipd/sigcheck.c:9-164 and the field extraction of wire/peer_wiregen.c for the three gossip messages):
+ *      blob = concatenated raw wire messages (2-byte type included), msg_off/msg_len locate them.  The device finds
+ *      the signatures, keys and signed regions itself, hashes (SHA-256d) and verifies.  status[m] = 0 all signatures
+ *      good; 1..4 = first bad signature in the reference's order (node_signature_1, node_signature_2,
+ *      bitcoin_signature_1, bitcoin_signature_2; node_announcement / channel_update: 1); -1 = not a gossip message or
+ *      too short.  channel_update is signed by a node the caller looks up in its gossmap: cu_signers33[m] (33 bytes per
+ *      MESSAGE, ignored for other types; NULL if the batch has no channel_update). ---- */
+int sv_verify_gossip_host(sv_ctx *ctx, const uint8_t *blob, size_t blob_len, const uint64_t *msg_off,
+                          const uint32_t *msg_len, size_t n_msgs, const uint8_t *cu_signers33, int *status);
+
 /* ---- DEVICE buffers (same SoA layout, device pointers); asynchronous on `stream`
  *      (a cudaStream_t passed as void*; NULL = the context's own stream).  d_verdicts[n] bytes;
  *      d_bitmap, if non-NULL, receives ceil(n/32) little-endian 32-bit words, bit i%32 of word i/32. ---- */

@@ -127,123 +127,38 @@ void check_tx_sigs_batch(const struct sha256_double *hashes, const struct bitcoi
     free(buf);
 }
 
-/* ---- gossip: slice raw wire messages the way gossipd/sigcheck.c does and verify them as one batch ---- */
-typedef struct {
-    uint64_t *off;
-    uint32_t *len;
-    u8 *key, *sig, *verdict;
-    size_t *owner;
-    size_t n, cap;
-} items_t;
-
-static void items_init(items_t *it, size_t cap) {
-    it->cap = cap ? cap : 1;
-    it->n = 0;
-    it->off = (uint64_t *)malloc(it->cap * sizeof(uint64_t));
-    it->len = (uint32_t *)malloc(it->cap * sizeof(uint32_t));
-    it->key = (u8 *)malloc(it->cap * 33);
-    it->sig = (u8 *)malloc(it->cap * 64);
-    it->verdict = (u8 *)calloc(it->cap, 1);
-    it->owner = (size_t *)malloc(it->cap * sizeof(size_t));
-    if (!it->off || !it->len || !it->key || !it->sig || !it->verdict || !it->owner) die("malloc", -3);
-}
-static void items_free(items_t *it) {
-    free(it->off); free(it->len); free(it->key); free(it->sig); free(it->verdict); free(it->owner);
-}
-static void items_add(items_t *it, uint64_t off, uint32_t len, const u8 *key33, const u8 *sig64, size_t owner) {
-    size_t i = it->n++;
-    it->off[i] = off; it->len[i] = len; it->owner[i] = owner;
-    memcpy(it->key + 33 * i, key33, 33);
-    memcpy(it->sig + 64 * i, sig64, 64);
-}
-static uint16_t be16(const u8 *p) { return (uint16_t)((p[0] << 8) | p[1]); }
-
-static void run_items(items_t *it, const u8 *blob, size_t blob_len) {
-    if (it->n == 0) return;
-    int rc = sv_verify_host_raw(ctx(), SV_KIND_ECDSA33, blob, blob_len, it->off, it->len, it->key, it->sig, it->n,
-                                it->verdict);
-    if (rc != SV_OK) die("sv_verify_host_raw", rc);
-}
-
-/* concatenates the messages; returns the blob and fills starts[] */
-static u8 *concat(const u8 *const *msgs, const size_t *lens, size_t n, uint64_t *starts, size_t *total) {
+/* ---- gossip: the raw wire messages go to the device as one blob; the DEVICE slices them the way
+ * gossipd/sigcheck.c does (k_gossip_slice), hashes the signed regions and verifies (sv_verify_gossip_host) ---- */
+static void gossip_batch(const u8 *const *msgs, const size_t *lens, size_t n, const struct node_id *signers,
+                         uint16_t want_type, int *status) {
+    if (n == 0) return;
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) total += lens[i];
+    u8 *blob = (u8 *)malloc(total ? total : 1);
+    uint64_t *off = (uint64_t *)malloc(n * sizeof(uint64_t));
+    uint32_t *len = (uint32_t *)malloc(n * sizeof(uint32_t));
+    if (!blob || !off || !len) die("malloc", -3);
     size_t t = 0;
-    for (size_t i = 0; i < n; i++) { starts[i] = t; t += lens[i]; }
-    u8 *blob = (u8 *)malloc(t ? t : 1);
-    if (!blob) die("malloc", -3);
-    for (size_t i = 0; i < n; i++) memcpy(blob + starts[i], msgs[i], lens[i]);
-    *total = t;
-    return blob;
+    for (size_t i = 0; i < n; i++) {
+        off[i] = t;
+        len[i] = (uint32_t)lens[i];
+        memcpy(blob + t, msgs[i], lens[i]);
+        t += lens[i];
+    }
+    int rc = sv_verify_gossip_host(ctx(), blob, total, off, len, n, signers ? signers[0].k : NULL, status);
+    if (rc != SV_OK) die("sv_verify_gossip_host", rc);
+    for (size_t i = 0; i < n; i++) /* this entry point is typed: a message of another kind is malformed here */
+        if (lens[i] < 2 || (uint16_t)((msgs[i][0] << 8) | msgs[i][1]) != want_type) status[i] = -1;
+    free(blob); free(off); free(len);
 }
 
 void sigcheck_channel_announcement_batch(const u8 *const *msgs, const size_t *lens, size_t n, int *status) {
-    /* wire/peer_wire.csv:340-352: type(2) sig x4 (2,66,130,194) flen(2)@258 features chain_hash(32) scid(8)
-     * node_id_1 node_id_2 bitcoin_key_1 bitcoin_key_2 (33 each).  Signed region: msg[258:] (sigcheck.c:75). */
-    uint64_t *starts = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
-    size_t total;
-    u8 *blob = concat(msgs, lens, n, starts, &total);
-    items_t it;
-    items_init(&it, 4 * n);
-    for (size_t i = 0; i < n; i++) {
-        const u8 *m = msgs[i];
-        status[i] = 0;
-        if (lens[i] < 260 || be16(m) != 256) { status[i] = -1; continue; }
-        size_t flen = be16(m + 258), keys = 260 + flen + 32 + 8;
-        if (lens[i] < keys + 4 * 33) { status[i] = -1; continue; }
-        for (int k = 0; k < 4; k++)
-            items_add(&it, starts[i] + 258, (uint32_t)(lens[i] - 258), m + keys + 33 * k, m + 2 + 64 * k, i);
-    }
-    run_items(&it, blob, total);
-    for (size_t j = 0, k = 0; j < it.n; j++) {
-        size_t o = it.owner[j];
-        k = (j > 0 && it.owner[j - 1] == o) ? k + 1 : 0;
-        if (!it.verdict[j] && status[o] == 0) status[o] = (int)k + 1; /* first failure wins (sigcheck.c:79-112) */
-    }
-    items_free(&it);
-    free(blob);
-    free(starts);
+    gossip_batch(msgs, lens, n, NULL, 256, status);
 }
-
 void sigcheck_node_announcement_batch(const u8 *const *msgs, const size_t *lens, size_t n, int *status) {
-    /* type(2) sig(64) flen(2)@66 features timestamp(4) node_id(33) ...; signed region msg[66:] (sigcheck.c:141) */
-    uint64_t *starts = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
-    size_t total;
-    u8 *blob = concat(msgs, lens, n, starts, &total);
-    items_t it;
-    items_init(&it, n);
-    for (size_t i = 0; i < n; i++) {
-        const u8 *m = msgs[i];
-        status[i] = 0;
-        if (lens[i] < 68 || be16(m) != 257) { status[i] = -1; continue; }
-        size_t flen = be16(m + 66), id = 68 + flen + 4;
-        if (lens[i] < id + 33) { status[i] = -1; continue; }
-        items_add(&it, starts[i] + 66, (uint32_t)(lens[i] - 66), m + id, m + 2, i);
-    }
-    run_items(&it, blob, total);
-    for (size_t j = 0; j < it.n; j++)
-        if (!it.verdict[j]) status[it.owner[j]] = 1;
-    items_free(&it);
-    free(blob);
-    free(starts);
+    gossip_batch(msgs, lens, n, NULL, 257, status);
 }
-
 void sigcheck_channel_update_batch(const u8 *const *msgs, const size_t *lens, const struct node_id *signers,
                                    size_t n, int *status) {
-    /* type(2) sig(64) chain_hash(32) scid(8) ...; signed region msg[66:] (sigcheck.c:33) */
-    uint64_t *starts = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
-    size_t total;
-    u8 *blob = concat(msgs, lens, n, starts, &total);
-    items_t it;
-    items_init(&it, n);
-    for (size_t i = 0; i < n; i++) {
-        status[i] = 0;
-        if (lens[i] < 66 + 32 + 8 || be16(msgs[i]) != 258) { status[i] = -1; continue; }
-        items_add(&it, starts[i] + 66, (uint32_t)(lens[i] - 66), signers[i].k, msgs[i] + 2, i);
-    }
-    run_items(&it, blob, total);
-    for (size_t j = 0; j < it.n; j++)
-        if (!it.verdict[j]) status[it.owner[j]] = 1;
-    items_free(&it);
-    free(blob);
-    free(starts);
+    gossip_batch(msgs, lens, n, signers, 258, status); /* struct node_id is exactly 33 bytes: signers[] is the packed array */
 }

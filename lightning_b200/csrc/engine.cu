@@ -67,12 +67,13 @@ __global__ void __launch_bounds__(64) k_prep_ecdsa(const u8* msg, const u8* sig,
     if (base >= n) return;
     int cnt = (int)((n - base < SV_PREP_BATCH) ? (n - base) : SV_PREP_BATCH);
     sc sv[SV_PREP_BATCH];
-    u32 okmask = 0;
+    u32 okmask = 0, parsedmask = 0;
 #pragma unroll 1
     for (int j = 0; j < SV_PREP_BATCH; j++) {
         sc r, s, m;
-        bool ok = false;
-        if (j < cnt) ok = ecdsa_parse(r, s, m, sig + 64 * (base + j), msg + 32 * (base + j));
+        bool ok = false, parsed = false;
+        if (j < cnt) ok = ecdsa_parse(r, s, m, sig + 64 * (base + j), msg + 32 * (base + j), &parsed);
+        parsedmask |= (parsed ? 1u : 0u) << j;
         if (!ok) {
 #pragma unroll
             for (int k = 0; k < 8; k++) s.v[k] = (k == 0);
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(64) k_prep_ecdsa(const u8* msg, const u8* sig,
         sc r, s, m;
         (void)ecdsa_parse(r, s, m, sig + 64 * (base + j), msg + 32 * (base + j));
         sv_work w;
-        ecdsa_finish_prep(w, (okmask >> j) & 1u, r, m, sv[j]);
+        ecdsa_finish_prep(w, (okmask >> j) & 1u, r, m, sv[j], (parsedmask >> j) & 1u);
         work[base + j] = w;
     }
 }
@@ -109,7 +110,7 @@ __device__ sv_work g_idle_work = {{1, 0, 0, 0, 0}, {1, 0, 0, 0, 0}, {0}, 0, {0}}
 template <int KIND>
 __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main(sv_work* work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
-           const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict) {
+           const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict, u8* keyok) {
     const size_t keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -130,10 +131,86 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
             ecmult_uniform(R, w, Q, gtab, tab);
             if (active) schnorr_park(reinterpret_cast<sv_jac*>(work + i), R, ok);
         } else {
-            u32 v = verify_curve_side(KIND, w, key + keylen * j, sig + 64 * j, gtab, tab);
-            if (active) verdict[i] = (u8)v;
+            bool kd;
+            u32 v = verify_curve_side(KIND, w, key + keylen * j, sig + 64 * j, gtab, tab, &kd);
+            if (active) {
+                verdict[i] = (u8)v;
+                if (keyok) keyok[i] = kd ? 1 : 0;  // gossip ingest distinguishes "undecodable key" (malformed message)
+            }
         }
     }
+}
+
+// ---- gossip ingest: the device slices raw wire messages itself ----------------------------
+// One thread per message.  Field offsets: wire/peer_wire.csv:340-377; signed regions and checking order:
+// gossipd/sigcheck.c:9-43 (channel_update), 45-115 (channel_announcement), 118-164 (node_announcement).
+// item_base[m] is the first item slot of message m (4 slots for a channel_announcement, 1 otherwise, host-computed
+// from the 2-byte type).  Writes span (off,len), key33, sig64 per item; status[m] = -1 if malformed.
+__global__ void __launch_bounds__(128) k_gossip_slice(const u8* blob, const u64* msg_off, const u32* msg_len,
+                                                      const u32* item_base, const u8* signers33, size_t n_msgs,
+                                                      u64* span_off, u32* span_len, u8* key33, u8* sig64, int* status) {
+    size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_msgs) return;
+    const u8* p = blob + msg_off[m];
+    u32 len = msg_len[m];
+    u32 type = len >= 2 ? (((u32)p[0] << 8) | p[1]) : 0;
+    u32 base = item_base[m];
+    int nitems = (type == 256) ? 4 : ((type == 257 || type == 258) ? 1 : 0);
+    int st = 0;
+    u32 hoff = (type == 256) ? 258 : 66;
+    u32 keys = 0;
+    if (type == 256) {
+        if (len < 260) st = -1;
+        else {
+            u32 flen = ((u32)p[258] << 8) | p[259];
+            keys = 260 + flen + 32 + 8;
+            if (len < keys + 4 * 33) st = -1;
+        }
+    } else if (type == 257) {
+        if (len < 68) st = -1;
+        else {
+            u32 flen = ((u32)p[66] << 8) | p[67];
+            keys = 68 + flen + 4;
+            if (len < keys + 33) st = -1;
+        }
+    } else if (type == 258) {
+        if (len < 66 + 32 + 8 || signers33 == nullptr) st = -1;
+    } else {
+        st = -1;
+    }
+    for (int k = 0; k < nitems; k++) {
+        u32 it = base + k;
+        bool ok = (st == 0);
+        span_off[it] = msg_off[m] + (ok ? hoff : 0);
+        span_len[it] = ok ? (len - hoff) : 0;
+        const u8* kp = (type == 258) ? (signers33 ? signers33 + 33 * m : p) : (p + keys + 33 * k);
+        for (int b = 0; b < 33; b++) key33[33 * (size_t)it + b] = ok ? kp[b] : 0;  // an all-zero key never verifies
+        const u8* sp = p + 2 + 64 * k;
+        for (int b = 0; b < 64; b++) sig64[64 * (size_t)it + b] = ok ? sp[b] : 0;
+    }
+    status[m] = st;
+}
+// status[m] = 1 + index of the first failing signature (the reference's order), 0 if all verify
+// -1 also when CLN's wire parser would refuse the message: a signature with r >= n or s >= n
+// (fromwire_secp256k1_ecdsa_signature, wire/fromwire.c:188-199) or an undecodable bitcoin_key (fromwire_pubkey,
+// bitcoin/pubkey.c:102-113).  node_ids are raw bytes on the wire (common/node_id.c:54) and only fail the signature.
+__global__ void __launch_bounds__(128) k_gossip_status(const u8* blob, const u64* msg_off, const u32* msg_len,
+                                                       const u32* item_base, size_t n_msgs, const u8* verdict,
+                                                       const sv_work* work, const u8* keyok, int* status) {
+    size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_msgs || status[m] != 0) return;
+    const u8* p = blob + msg_off[m];
+    u32 type = ((u32)p[0] << 8) | p[1];
+    int nitems = (type == 256) ? 4 : 1;
+    int st = 0;
+    for (int k = nitems - 1; k >= 0; k--)
+        if (!verdict[item_base[m] + k]) st = k + 1;
+    for (int k = 0; k < nitems; k++) {
+        u32 it = item_base[m] + k;
+        if (!(work[it].flags & SV_WF_PARSED)) st = -1;
+        if (type == 256 && k >= 2 && !keyok[it]) st = -1;
+    }
+    status[m] = st;
 }
 
 static_assert(sizeof(sv_jac) == sizeof(sv_work), "R is parked in place of the work record");
@@ -587,7 +664,7 @@ extern "C" int sv_get_info(const sv_ctx* ctx, sv_info* info) {
 
 // launch prep + main on device-resident SoA arrays
 static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
-                         u8* d_verdict, u32* d_bitmap, cudaStream_t st) {
+                         u8* d_verdict, u32* d_bitmap, cudaStream_t st, u8* d_keyok = nullptr) {
     if (n == 0) return SV_OK;
     int rc = ensure_work(ctx, n);
     if (rc) return rc;
@@ -602,12 +679,12 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
     if (kind == SV_KIND_ECDSA33)
-        k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+        k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict, d_keyok);
     else if (kind == SV_KIND_ECDSA_XY)
-        k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+        k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict, d_keyok);
     else
     {
-        k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict);
+        k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict, d_keyok);
         size_t threads = (n + SV_FINAL_BATCH - 1) / SV_FINAL_BATCH;
         k_final_schnorr<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_work, d_sig, n, d_verdict);
         ctx->launches += 1;
@@ -777,6 +854,71 @@ extern "C" int sv_pubkey_parse_host(sv_ctx* ctx, const uint8_t* key33, size_t n,
     CK(cudaMemcpyAsync(xy64, ctx->d_sig, 64 * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ok, ctx->d_verdict, n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SV_OK;
+}
+
+// gossip ingest with device-side slicing: blob = concatenated wire messages, msg_off/msg_len locate them.
+extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t blob_len, const uint64_t* msg_off,
+                                     const uint32_t* msg_len, size_t n_msgs, const uint8_t* cu_signers33, int* status) {
+    if (!ctx || (n_msgs && (!blob || !msg_off || !msg_len || !status))) return SV_ERR_ARG;
+    if (n_msgs == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    // the host only reads the 2-byte type of each message to lay out the item slots
+    std::vector<u32> base(n_msgs);
+    size_t items = 0;
+    for (size_t m = 0; m < n_msgs; m++) {
+        if (msg_off[m] > blob_len || msg_len[m] > blob_len - msg_off[m]) return fail(ctx, SV_ERR_ARG, "message out of range", cudaSuccess);
+        u32 type = msg_len[m] >= 2 ? (((u32)blob[msg_off[m]] << 8) | blob[msg_off[m] + 1]) : 0;
+        base[m] = (u32)items;
+        items += (type == 256) ? 4 : ((type == 257 || type == 258) ? 1 : 0);
+    }
+    size_t cap = items ? items : 1;
+    int rc = ensure_staging(ctx, cap);
+    if (rc) return rc;
+    if (blob_len > ctx->data_cap) {
+        cudaFree(ctx->d_data); ctx->d_data = nullptr; ctx->data_cap = 0;
+        CK(cudaMalloc(&ctx->d_data, blob_len));
+        ctx->data_cap = blob_len;
+    }
+    size_t need = (cap > n_msgs ? cap : n_msgs);
+    if (need > ctx->span_cap) {
+        cudaFree(ctx->d_off); cudaFree(ctx->d_len); ctx->d_off = nullptr; ctx->d_len = nullptr; ctx->span_cap = 0;
+        CK(cudaMalloc(&ctx->d_off, need * sizeof(u64)));
+        CK(cudaMalloc(&ctx->d_len, need * sizeof(u32)));
+        ctx->span_cap = need;
+    }
+    u64* d_moff = nullptr; u32 *d_mlen = nullptr, *d_base = nullptr; int* d_status = nullptr; u8 *d_signers = nullptr, *d_keyok = nullptr;
+    CK(cudaMalloc(&d_keyok, cap));
+    CK(cudaMalloc(&d_moff, n_msgs * sizeof(u64)));
+    CK(cudaMalloc(&d_mlen, n_msgs * sizeof(u32)));
+    CK(cudaMalloc(&d_base, n_msgs * sizeof(u32)));
+    CK(cudaMalloc(&d_status, n_msgs * sizeof(int)));
+    if (cu_signers33) CK(cudaMalloc(&d_signers, n_msgs * 33));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_data, blob, blob_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_moff, msg_off, n_msgs * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_mlen, msg_len, n_msgs * sizeof(u32), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_base, base.data(), n_msgs * sizeof(u32), cudaMemcpyHostToDevice, st));
+    if (cu_signers33) CK(cudaMemcpyAsync(d_signers, cu_signers33, n_msgs * 33, cudaMemcpyHostToDevice, st));
+    unsigned gm = (unsigned)((n_msgs + 127) / 128);
+    k_gossip_slice<<<gm, 128, 0, st>>>(ctx->d_data, d_moff, d_mlen, d_base, d_signers, n_msgs, ctx->d_off, ctx->d_len,
+                                       ctx->d_key, ctx->d_sig, d_status);
+    ctx->launches += 1;
+    if (items) {
+        k_sha256d<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(ctx->d_data, ctx->d_off, ctx->d_len, items, ctx->d_msg);
+        ctx->launches += 1;
+        rc = launch_verify(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, nullptr, st, d_keyok);
+        if (rc == SV_OK) {
+            k_gossip_status<<<gm, 128, 0, st>>>(ctx->d_data, d_moff, d_mlen, d_base, n_msgs, ctx->d_verdict, ctx->d_work,
+                                                d_keyok, d_status);
+            ctx->launches += 1;
+        }
+    }
+    cudaError_t ce = cudaMemcpyAsync(status, d_status, n_msgs * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d_moff); cudaFree(d_mlen); cudaFree(d_base); cudaFree(d_status); cudaFree(d_signers); cudaFree(d_keyok);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "gossip ingest", ce);
     return SV_OK;
 }
 

@@ -245,6 +245,7 @@ struct sv_work {
 };
 #define SV_WF_VALID 1u       // scalar-side checks passed (range checks; s != 0 ...)
 #define SV_WF_R_PLUS_N 2u    // ECDSA: r < p - n, so r + n is a second x candidate
+#define SV_WF_PARSED 4u      // r < n and s < n: secp256k1_ecdsa_signature_parse_compact would accept the encoding
 
 // 160-bit two's complement helpers (5 limbs)
 SV_HD void s160_add(u32 r[5], const u32 a[5], const u32 b[5]) {

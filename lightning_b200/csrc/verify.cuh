@@ -92,11 +92,12 @@ SV_HD void fe_to_words(u32* p, const fe& a) {
 // ECDSA: parse (r,s) and the message hash.  Returns false (verdict 0) for r >= n, s >= n
 // (parse_compact, secp256k1.c:388-392), r == 0, s == 0 (ecdsa_impl.h:204), s > n/2
 // (secp256k1.c:451).  The message is reduced mod n and never rejected (secp256k1.c:449).
-SV_HD bool ecdsa_parse(sc& r, sc& s, sc& m, const u8* sig64, const u8* msg32) {
+SV_HD bool ecdsa_parse(sc& r, sc& s, sc& m, const u8* sig64, const u8* msg32, bool* parsed = nullptr) {
     bool ovr, ovs;
     sc_set_b32(r, sig64, &ovr);
     sc_set_b32(s, sig64 + 32, &ovs);
     sc_set_b32(m, msg32, nullptr);
+    if (parsed) *parsed = !ovr && !ovs;  // what CLN's wire layer checks (wire/fromwire.c:188-199)
     bool ok = !ovr && !ovs && !sc_is_zero(r) && !sc_is_zero(s) && !sc_is_high(s);
     return ok;
 }
@@ -112,9 +113,10 @@ SV_HD void work_set_invalid(sv_work& w) {
 }
 
 // ECDSA: given s^-1, finish the record: u1 = m/s, u2 = r/s (ecdsa_impl.h:209-211)
-SV_HD void ecdsa_finish_prep(sv_work& w, bool ok, const sc& r, const sc& m, const sc& sinv) {
+SV_HD void ecdsa_finish_prep(sv_work& w, bool ok, const sc& r, const sc& m, const sc& sinv, bool parsed = true) {
     if (!ok) {
         work_set_invalid(w);
+        w.flags = parsed ? SV_WF_PARSED : 0u;
         return;
     }
     sc u1, u2;
@@ -126,7 +128,7 @@ SV_HD void ecdsa_finish_prep(sv_work& w, bool ok, const sc& r, const sc& m, cons
     const u32 pmn[8] = {0x2FC9BAEEu, 0x402DA172u, 0x50B75FC4u, 0x45512319u, 0x00000001u, 0, 0, 0};
     u32 t[8];
     u32 bw = u256_sub(t, r.v, pmn);
-    w.flags = SV_WF_VALID | (bw ? SV_WF_R_PLUS_N : 0u);
+    w.flags = SV_WF_VALID | SV_WF_PARSED | (bw ? SV_WF_R_PLUS_N : 0u);
     SV_UNROLL
     for (int i = 0; i < 5; i++) w.pad[i] = 0;
 }
@@ -429,11 +431,13 @@ SV_HD void schnorr_final_batch(u8* verdict, const sv_jac* jac, const u8* sig64, 
 
 // whole curve side for one item
 SV_HD u32 verify_curve_side(int kind, const sv_work* w, const u8* key, const u8* sig64, const ge_mem* gtab,
-                            qtab_entry* tab) {
+                            qtab_entry* tab, bool* key_ok = nullptr) {
     u32 flags = w->flags;
     bool ok = (flags & SV_WF_VALID) != 0;  // an invalid record carries harmless dummy scalars (k1 = k2 = 1, u1 = 0)
     ge Q;
-    ok = key_decode(Q, kind, key) && ok;
+    bool kd = key_decode(Q, kind, key);
+    if (key_ok) *key_ok = kd;
+    ok = kd && ok;
     gej R;
     ecmult_uniform(R, w, Q, gtab, tab);
     u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);

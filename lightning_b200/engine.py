@@ -48,6 +48,7 @@ def load_library():
     lib.sv_verify_host.argtypes = [vp, i, vp, vp, vp, sz, vp]
     lib.sv_verify_host_raw.argtypes = [vp, i, vp, sz, vp, vp, vp, vp, sz, vp]
     lib.sv_verify_device.argtypes = [vp, i, vp, vp, vp, sz, vp, vp, vp]
+    lib.sv_verify_gossip_host.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
     lib.sv_sync.argtypes = [vp, vp]
     lib.sv_get_stream.argtypes = [vp]
     lib.sv_set_profiling.argtypes = [vp, i]
@@ -147,6 +148,22 @@ class SigVerifier:
                                                 length.ctypes.data, key.ctypes.data, sig64.ctypes.data, n,
                                                 out.ctypes.data), "sv_verify_host_raw")
         return out
+
+    def verify_gossip(self, msgs, cu_signers=None):
+        """Raw gossip wire messages in, one status per message out (0 ok, 1..4 first bad signature, -1 malformed);
+        the device slices, hashes and verifies (gossipd/sigcheck.c, batched).  cu_signers: (n,33) or None."""
+        lens = np.array([len(m) for m in msgs], dtype=np.uint32)
+        offs = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64) if len(msgs) else np.zeros(0, np.uint64)
+        blob = np.frombuffer(b"".join(bytes(m) for m in msgs), dtype=np.uint8)
+        n = len(msgs)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        sg = None
+        if cu_signers is not None:
+            sg = _u8(cu_signers, 33)
+        self._check(self.lib.sv_verify_gossip_host(self._ctx, blob.ctypes.data, blob.size, offs.ctypes.data, lens.ctypes.data, n,
+                                                   sg.ctypes.data if sg is not None else None, status.ctypes.data),
+                    "sv_verify_gossip_host")
+        return status[:n]
 
     def sha256_double(self, data, off, length):
         data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)

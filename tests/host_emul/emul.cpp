@@ -157,7 +157,7 @@ void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, si
             bool ok[SV_PREP_BATCH];
             for (int j = 0; j < cnt; j++) {
                 sc s;
-                ok[j] = ecdsa_parse(r[j], s, m[j], sig + 64 * (base + j), msg + 32 * (base + j));
+                ok[j] = ecdsa_parse(r[j], s, m[j], sig + 64 * (base + j), msg + 32 * (base + j), nullptr);
                 if (!ok[j]) { memset(s.v, 0, 32); s.v[0] = 1; }
                 sv[j] = s;
             }
