@@ -65,6 +65,14 @@ bool pubkey_from_der(const u8 *der, size_t len, struct pubkey *key);
 void check_tx_sigs_batch(const struct sha256_double *hashes, const struct bitcoin_signature *sigs,
                          const struct pubkey *key, size_t n, bool *ok);
 
+/* The same loop with the BIP143 sighash ALSO computed on the device (row N2): check_tx_sig (bitcoin/signature.c:194-221)
+ * for n one-input one-output transactions described by sv_tx records (cln_sigverify.h); the sighash type of each
+ * signature is taken from sigs[i].sighash_type and gated exactly as check_tx_sig does (:206-211: only SIGHASH_ALL or
+ * SIGHASH_SINGLE|SIGHASH_ANYONECANPAY, else false). */
+struct sv_tx_fields; /* = sv_tx of cln_sigverify.h */
+void check_tx_sigs_bip143_batch(const void *sv_tx_array, const u8 *scripts, size_t scripts_len,
+                                const struct pubkey *key, const struct bitcoin_signature *sigs, size_t n, bool *ok);
+
 /* gossipd: status[i] = 0 if every signature of message i verifies, else 1 + the index of the FIRST bad
  * signature in the reference's checking order (channel_announcement: node_signature_1, node_signature_2,
  * bitcoin_signature_1, bitcoin_signature_2 -> 1..4; node_announcement / channel_update: 1); -1 if the

@@ -91,6 +91,23 @@ int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_l
 int sv_verify_gossip_host(sv_ctx *ctx, const uint8_t *blob, size_t blob_len, const uint64_t *msg_off,
                           const uint32_t *msg_len, size_t n_msgs, const uint8_t *cu_signers33, int *status);
 
+/* ---- check_tx_sig with the BIP143 sighash computed ON THE DEVICE.  Replaces, for the one-input
+ *      one-output commitment-HTLC transactions of channeld/channeld.c:2215-2232 (shape: common/htlc_tx.c:10-69),
+ *      bitcoin_tx_hash_for_sig (bitcoin/signature.c:120-151) -> wally_tx_get_btc_signature_hash ->
+ *      bip143_signature_hash (libwally tx_io.c:660-765) + check_signed_hash.  The host passes only the fields of the
+ *      preimage; scripts live in one blob.  sighash32_out (optional, n x 32) returns the computed sighashes. ---- */
+typedef struct {
+    uint32_t version, locktime, sequence, sighash_type; /* sighash_type: SIGHASH_ALL 1 / NONE 2 / SINGLE 3, | 0x80 ANYONECANPAY */
+    uint8_t prev_txid[32];                              /* as serialised in the transaction (internal byte order) */
+    uint32_t prev_index;
+    uint32_t script_off, script_len;                    /* witness script (scriptCode) inside `scripts` */
+    uint32_t out_script_off, out_script_len;            /* scriptPubKey of the single output inside `scripts` */
+    uint32_t pad;
+    uint64_t input_amount, output_amount;               /* satoshi */
+} sv_tx;
+int sv_verify_tx_host(sv_ctx *ctx, int kind, const sv_tx *txs, const uint8_t *scripts, size_t scripts_len,
+                      const uint8_t *key, const uint8_t *sig64, size_t n, uint8_t *verdicts, uint8_t *sighash32_out);
+
 /* ---- DEVICE buffers (same SoA layout, device pointers); asynchronous on `stream`
  *      (a cudaStream_t passed as void*; NULL = the context's own stream).  d_verdicts[n] bytes;
  *      d_bitmap, if non-NULL, receives ceil(n/32) little-endian 32-bit words, bit i%32 of word i/32. ---- */

@@ -127,6 +127,31 @@ void check_tx_sigs_batch(const struct sha256_double *hashes, const struct bitcoi
     free(buf);
 }
 
+void check_tx_sigs_bip143_batch(const void *sv_tx_array, const u8 *scripts, size_t scripts_len,
+                                const struct pubkey *key, const struct bitcoin_signature *sigs, size_t n, bool *ok) {
+    if (n == 0) return;
+    sv_tx *txs = (sv_tx *)malloc(n * sizeof(sv_tx));
+    u8 *buf = (u8 *)malloc(n * (64 + 64 + 1));
+    if (!txs || !buf) die("malloc", -3);
+    memcpy(txs, sv_tx_array, n * sizeof(sv_tx));
+    u8 *xy = buf, *sig = buf + 64 * n, *v = sig + 64 * n;
+    for (size_t i = 0; i < n; i++) {
+        txs[i].sighash_type = (uint32_t)sigs[i].sighash_type; /* the type committed to is the signature's */
+        pubkey_to_xy(xy + 64 * i, &key->pubkey);
+        sig_to_wire(sig + 64 * i, &sigs[i].s);
+    }
+    int rc = sv_verify_tx_host(ctx(), SV_KIND_ECDSA_XY, txs, scripts, scripts_len, xy, sig, n, v, NULL);
+    if (rc != SV_OK) die("sv_verify_tx_host", rc);
+    for (size_t i = 0; i < n; i++) {
+        /* check_tx_sig's gate (signature.c:206-211); a witness script is always present on this path */
+        bool type_ok = sigs[i].sighash_type == SIGHASH_ALL ||
+                       (int)sigs[i].sighash_type == (SIGHASH_SINGLE | SIGHASH_ANYONECANPAY);
+        ok[i] = type_ok && v[i] == 1;
+    }
+    free(txs);
+    free(buf);
+}
+
 /* ---- gossip: the raw wire messages go to the device as one blob; the DEVICE slices them the way
  * gossipd/sigcheck.c does (k_gossip_slice), hashes the signed regions and verifies (sv_verify_gossip_host) ---- */
 static void gossip_batch(const u8 *const *msgs, const size_t *lens, size_t n, const struct node_id *signers,

@@ -141,6 +141,18 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     }
 }
 
+// ---- device-side BIP143: one thread per transaction input -> msg32 ----------------------
+__global__ void __launch_bounds__(128) k_bip143(const sv_tx_item* txs, const u8* blob, size_t n, u8* msg32, u8* okout) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    okout[i] = bip143_sighash(msg32 + 32 * i, txs[i], blob) ? 1 : 0;
+}
+// force verdict 0 where the sighash could not be formed
+__global__ void k_mask_verdicts(u8* verdict, const u8* ok, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !ok[i]) verdict[i] = 0;
+}
+
 // ---- gossip ingest: the device slices raw wire messages itself ----------------------------
 // One thread per message.  Field offsets: wire/peer_wire.csv:340-377; signed regions and checking order:
 // gossipd/sigcheck.c:9-43 (channel_update), 45-115 (channel_announcement), 118-164 (node_announcement).
@@ -919,6 +931,53 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
     cudaFree(d_moff); cudaFree(d_mlen); cudaFree(d_base); cudaFree(d_status); cudaFree(d_signers); cudaFree(d_keyok);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "gossip ingest", ce);
+    return SV_OK;
+}
+
+// check_tx_sig with the BIP143 sighash computed on the device (channeld's per-HTLC loop as one launch)
+static_assert(sizeof(sv_tx_item) == sizeof(sv_tx), "host and device views of the transaction item must agree");
+extern "C" int sv_verify_tx_host(sv_ctx* ctx, int kind, const sv_tx* txs, const uint8_t* scripts, size_t scripts_len,
+                                 const uint8_t* key, const uint8_t* sig64, size_t n, uint8_t* verdicts,
+                                 uint8_t* sighash32_out) {
+    size_t ks = sv_key_size(kind);
+    if (!ctx || ks == 0 || kind == SV_KIND_SCHNORR || (n && (!txs || !key || !sig64 || !verdicts))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    for (size_t i = 0; i < n; i++)
+        if ((size_t)txs[i].script_off + txs[i].script_len > scripts_len ||
+            (size_t)txs[i].out_script_off + txs[i].out_script_len > scripts_len)
+            return fail(ctx, SV_ERR_ARG, "script span out of range", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    if (scripts_len + 1 > ctx->data_cap) {
+        cudaFree(ctx->d_data); ctx->d_data = nullptr; ctx->data_cap = 0;
+        CK(cudaMalloc(&ctx->d_data, scripts_len + 1));
+        ctx->data_cap = scripts_len + 1;
+    }
+    sv_tx_item* d_txs = nullptr;
+    u8* d_ok = nullptr;
+    CK(cudaMalloc(&d_txs, n * sizeof(sv_tx_item)));
+    CK(cudaMalloc(&d_ok, n));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_txs, txs, n * sizeof(sv_tx_item), cudaMemcpyHostToDevice, st));
+    if (scripts_len) CK(cudaMemcpyAsync(ctx->d_data, scripts, scripts_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_key, key, ks * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_sig, sig64, 64 * n, cudaMemcpyHostToDevice, st));
+    k_bip143<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_txs, ctx->d_data, n, ctx->d_msg, d_ok);
+    ctx->launches += 1;
+    rc = launch_verify(ctx, kind, ctx->d_msg, ctx->d_key, ctx->d_sig, n, ctx->d_verdict, nullptr, st);
+    cudaError_t ce = cudaSuccess;
+    if (rc == SV_OK) {
+        k_mask_verdicts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_verdict, d_ok, n);
+        ctx->launches += 1;
+        ce = cudaMemcpyAsync(verdicts, ctx->d_verdict, n, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && sighash32_out) ce = cudaMemcpyAsync(sighash32_out, ctx->d_msg, 32 * n, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    }
+    cudaFree(d_txs);
+    cudaFree(d_ok);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "sv_verify_tx_host", ce);
     return SV_OK;
 }
 

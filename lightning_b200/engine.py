@@ -25,6 +25,15 @@ class EngineError(RuntimeError):
     pass
 
 
+class SvTx(ctypes.Structure):
+    """sv_tx (include/cln_sigverify.h): the BIP143-relevant fields of a one-input one-output segwit transaction."""
+    _fields_ = [("version", ctypes.c_uint32), ("locktime", ctypes.c_uint32), ("sequence", ctypes.c_uint32),
+                ("sighash_type", ctypes.c_uint32), ("prev_txid", ctypes.c_uint8 * 32), ("prev_index", ctypes.c_uint32),
+                ("script_off", ctypes.c_uint32), ("script_len", ctypes.c_uint32), ("out_script_off", ctypes.c_uint32),
+                ("out_script_len", ctypes.c_uint32), ("pad", ctypes.c_uint32), ("input_amount", ctypes.c_uint64),
+                ("output_amount", ctypes.c_uint64)]
+
+
 class SvInfo(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("sm_count", ctypes.c_int), ("main_block", ctypes.c_int),
                 ("main_grid", ctypes.c_int), ("main_regs", ctypes.c_int), ("gtable_bytes", ctypes.c_size_t),
@@ -49,6 +58,7 @@ def load_library():
     lib.sv_verify_host_raw.argtypes = [vp, i, vp, sz, vp, vp, vp, vp, sz, vp]
     lib.sv_verify_device.argtypes = [vp, i, vp, vp, vp, sz, vp, vp, vp]
     lib.sv_verify_gossip_host.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
+    lib.sv_verify_tx_host.argtypes = [vp, i, vp, vp, sz, vp, vp, sz, vp, vp]
     lib.sv_sync.argtypes = [vp, vp]
     lib.sv_get_stream.argtypes = [vp]
     lib.sv_set_profiling.argtypes = [vp, i]
@@ -164,6 +174,20 @@ class SigVerifier:
                                                    sg.ctypes.data if sg is not None else None, status.ctypes.data),
                     "sv_verify_gossip_host")
         return status[:n]
+
+    def check_tx_sigs(self, kind, txs, scripts, key, sig64, want_sighash=False):
+        """check_tx_sig (bitcoin/signature.c:194) for n one-input one-output transactions with the BIP143 sighash
+        computed on the device.  txs: ctypes array of SvTx; scripts: bytes blob; key (n, keysize); sig64 (n, 64)."""
+        n = len(txs)
+        key = _u8(key, KEY_SIZE[kind])
+        sig64 = _u8(sig64, 64)
+        blob = np.frombuffer(bytes(scripts) if len(scripts) else b"\0", dtype=np.uint8)
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        sh = np.zeros((max(n, 1), 32), dtype=np.uint8)
+        self._check(self.lib.sv_verify_tx_host(self._ctx, kind, ctypes.addressof(txs), blob.ctypes.data, len(scripts),
+                                               key.ctypes.data, sig64.ctypes.data, n, out.ctypes.data,
+                                               sh.ctypes.data if want_sighash else None), "sv_verify_tx_host")
+        return (out[:n], sh[:n]) if want_sighash else out[:n]
 
     def sha256_double(self, data, off, length):
         data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)

@@ -171,3 +171,21 @@ int cln_sigcheck_channel_update(const u8 *msg, size_t len, const u8 *node_id33) 
     sweep();
     return r;
 }
+
+/* ---- BIP143 sighash exactly as bitcoin_tx_hash_for_sig obtains it (bitcoin/signature.c:120-151): build the
+ * one-input one-output transaction with libwally and call wally_tx_get_btc_signature_hash(..., USE_WITNESS).
+ * Returns 0 on success (WALLY_OK). ---- */
+#include <wally_transaction.h>
+int cln_htlc_sighash(uint32_t version, uint32_t locktime, const u8 *prev_txid32, uint32_t prev_index, uint32_t sequence,
+                     const u8 *wscript, size_t wscript_len, uint64_t input_amount, uint64_t output_amount,
+                     const u8 *out_script, size_t out_script_len, uint32_t sighash_type, u8 *out32) {
+    struct wally_tx *tx = NULL;
+    int rc = wally_tx_init_alloc(version, locktime, 1, 1, &tx);
+    if (rc) return rc;
+    rc = wally_tx_add_raw_input(tx, prev_txid32, 32, prev_index, sequence, NULL, 0, NULL, 0);
+    if (!rc) rc = wally_tx_add_raw_output(tx, output_amount, out_script, out_script_len, 0);
+    if (!rc) rc = wally_tx_get_btc_signature_hash(tx, 0, wscript, wscript_len, input_amount, sighash_type,
+                                                  WALLY_TX_FLAG_USE_WITNESS, out32, 32);
+    wally_tx_free(tx);
+    return rc;
+}

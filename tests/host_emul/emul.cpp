@@ -126,6 +126,13 @@ void emul_bip340_challenge(const u8* r32, const u8* px32, const u8* msg32, u8* o
     sha256_bip340_challenge(out32, r32, px32, msg32);
 }
 
+int emul_bip143(const void* tx_item, const u8* blob, u8* out32) {
+    sv_tx_item t;
+    memcpy(&t, tx_item, sizeof t);
+    return bip143_sighash(out32, t, blob) ? 1 : 0;
+}
+size_t emul_sizeof_tx_item(void) { return sizeof(sv_tx_item); }
+
 void emul_gtable_build(void) { build_gtable_fast(); }
 // entry computed the way the device kernel does it (double-and-add + Fermat), for cross-checking
 void emul_gtable_entry_device_algo(u32 e, u32* xy16) {

@@ -284,3 +284,29 @@ def test_gossip_device_side_slicing_vs_gossipd(engine, cln):
     got = engine.verify_gossip(batch, signers)
     assert list(got) == want
     assert want.count(0) > 600 and sum(1 for w in want if w > 0) > 50 and want.count(-1) >= 3
+
+
+def test_htlc_loop_device_side_bip143(engine, ref, cln):
+    """Row N2: channeld's per-HTLC loop with the BIP143 sighash computed on the device: 483 HTLC transactions signed by
+    one key (the reference signs libwally's sighash); sighashes must equal libwally's, verdicts the reference's."""
+    n = 483
+    rng = np.random.default_rng(77)
+    txs, blob = util.make_htlc_txs(rng, n)
+    sk = rng.integers(1, 256, size=32, dtype=np.uint8)
+    pub33, pubxy = np.zeros(33, np.uint8), np.zeros(64, np.uint8)
+    assert ref.ref_pubkey_create(P(sk), P(pub33), P(pubxy))
+    sig = np.zeros((n, 64), np.uint8)
+    want_hash = np.zeros((n, 32), np.uint8)
+    for i in range(n):
+        want_hash[i] = util.cln_sighash(cln, txs[i], blob)
+        assert ref.ref_ecdsa_sign(P(sk), P(want_hash[i]), P(sig[i]))
+    sig[100, 3] ^= 1
+    txs[200].output_amount += 1      # a different transaction than the one that was signed
+    txs[300].sighash_type = 0x183    # libwally refuses sighash bits above the low byte (tx_io.c:682) -> verdict 0
+    keys = np.tile(pubxy, (n, 1))
+    got, sh = engine.check_tx_sigs(1, txs, blob, keys, sig, want_sighash=True)
+    ok = np.ones(n, bool); ok[[100, 200, 300]] = False
+    assert np.array_equal(sh[[i for i in range(n) if i not in (200, 300)]], want_hash[[i for i in range(n) if i not in (200, 300)]])
+    assert np.array_equal(got.astype(bool), ok)
+    got33 = engine.check_tx_sigs(0, txs, blob, np.tile(pub33, (n, 1)), sig)
+    assert np.array_equal(got33, got)

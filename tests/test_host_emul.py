@@ -175,3 +175,16 @@ def test_full_verify_adversarial_scalars(emul, ref):
     msg2[:, 31] ^= 1
     want2 = util.ref_verify(ref, 0, msg2, pub33, sig)
     assert np.array_equal(emul_verify(emul, 0, msg2, pub33, sig), want2)
+
+
+def test_device_bip143_preimage_vs_libwally(emul, cln):
+    """Row N2: the device-side BIP143 sighash (host build of the kernel source) vs libwally's bip143_signature_hash."""
+    import lightning_b200 as L
+    assert emul.emul_sizeof_tx_item() == ctypes.sizeof(L.SvTx)
+    rng = np.random.default_rng(31)
+    txs, blob = util.make_htlc_txs(rng, 200)
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    for i in range(200):
+        out = np.zeros(32, np.uint8)
+        assert emul.emul_bip143(ctypes.byref(txs[i]), P(buf), P(out)) == 1
+        assert np.array_equal(out, util.cln_sighash(cln, txs[i], blob)), (i, txs[i].sighash_type)

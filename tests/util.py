@@ -117,3 +117,42 @@ def corrupt(w, every=10):
             w["sig"][i, 32:] = 0
             w["sig"][j % n, :32] = 255
     return w
+
+
+def make_htlc_txs(rng, n):
+    """n synthetic commitment-HTLC transaction inputs (shape: common/htlc_tx.c:10-69 — version 2, one input spending an
+    HTLC output of the commitment tx, one P2WSH output, nSequence 0/1, locktime 0 or a cltv expiry; witness script
+    sized like bitcoin/script.c:732/849 produce them; sighash ALL, or SINGLE|ANYONECANPAY with anchors
+    (channeld/channeld.c:1105-1108)), plus a few other sighash types.  Returns (SvTx array, scripts blob)."""
+    from lightning_b200 import SvTx
+    txs = (SvTx * n)()
+    blob = bytearray()
+    for i in range(n):
+        t = txs[i]
+        t.version = 2
+        t.locktime = int(rng.integers(0, 2)) * int(rng.integers(500000, 900000))
+        t.sequence = int(rng.integers(0, 2))
+        t.sighash_type = [1, 0x83, 1, 0x83, 2, 3, 0x81, 0x82][i % 8]
+        t.prev_txid[:] = list(rng.integers(0, 256, size=32, dtype=np.uint8))
+        t.prev_index = int(rng.integers(0, 600))
+        ws = bytes(rng.integers(0, 256, size=int(rng.integers(130, 145)) if i % 11 else int(rng.integers(0, 400)), dtype=np.uint8))
+        os_ = b"\x00\x20" + bytes(rng.integers(0, 256, size=32, dtype=np.uint8))
+        t.script_off, t.script_len = len(blob), len(ws)
+        blob += ws
+        t.out_script_off, t.out_script_len = len(blob), len(os_)
+        blob += os_
+        t.input_amount = int(rng.integers(546, 10**9))
+        t.output_amount = int(rng.integers(330, t.input_amount + 1))
+    return txs, bytes(blob)
+
+
+def cln_sighash(cln, t, blob):
+    """The same sighash from libwally (what bitcoin_tx_hash_for_sig computes), via oracle/cln_harness.c."""
+    out = np.zeros(32, np.uint8)
+    ws = blob[t.script_off:t.script_off + t.script_len]
+    os_ = blob[t.out_script_off:t.out_script_off + t.out_script_len]
+    rc = cln.cln_htlc_sighash(ctypes.c_uint32(t.version), ctypes.c_uint32(t.locktime), bytes(t.prev_txid), ctypes.c_uint32(t.prev_index),
+                              ctypes.c_uint32(t.sequence), ws, ctypes.c_size_t(len(ws)), ctypes.c_uint64(t.input_amount),
+                              ctypes.c_uint64(t.output_amount), os_, ctypes.c_size_t(len(os_)), ctypes.c_uint32(t.sighash_type), P(out))
+    assert rc == 0, rc
+    return out
