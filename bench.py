@@ -38,6 +38,10 @@ N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 BATCH = 1_000_000
 IMAD_PER_VERIFY = 125_440  # 1,960 field mults x 64
 BYTES_PER_VERIFY = 129.125
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_main<ECDSA33> launch over 1,000,000 verifications, from
+# `ncu --set full` (profiles/r1_k_main_1M_ncu_raw.csv): 766.8 MB + 562.9 MB.  ~10x the algorithmic 129 MB: the per-thread
+# Q-table slabs (768 B written + re-read per verification) and the 128-byte work records cycle through L2.
+NCU_DRAM_BYTES_PER_1M_LAUNCH = 766_794_752 + 562_898_944
 METRIC = "secp256k1 verifies/sec"
 
 
@@ -385,12 +389,14 @@ def run_engine(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "integer (IMAD.WIDE.U32 issue)", "achieved": achieved / 1e9, "peak": peak_imad / 1e9,
-                     "unit": "GIMAD/s", "frac": achieved / peak_imad, "traffic": None,
+                     "unit": "GIMAD/s", "frac": achieved / peak_imad,
+                     "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if n == 1_000_000 else None, "traffic_unit": "bytes/launch (ncu, profiles/r1_k_main_1M_ncu_raw.csv)",
                      "kernel": "k_main<ECDSA33>", "kernel_ms": main_avg, "prep_kernel_ms": prep_avg,
                      "algorithmic_imad_per_verify": IMAD_PER_VERIFY,
                      "peak_source": "measured live: engine probe k_probe_imad_wide (independent IMAD.WIDE.U32 chains)"},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": hbm_ach / hbm_peak, "traffic": None,
+                         "frac": hbm_ach / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if n == 1_000_000 else None,
+                         "achieved_incl_scratch": (NCU_DRAM_BYTES_PER_1M_LAUNCH / (main_avg * 1e-3) / 1e9) if n == 1_000_000 else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                          "note": "algorithmic bytes only (129.125 B/verify); the path is integer-compute bound"},
         "cpu_baseline": cpu,
