@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(128) k_sha256d(const u8* data, const u64* off,
     if (i < n) sha256d_bytes(out32 + 32 * i, data + off[i], len[i]);
 }
 
-// scalar side, ECDSA.  Each thread owns SV_PREP_BATCH consecutive signatures so that the single
-// Fermat exponentiation mod n is amortised by Montgomery's trick (3 mults per signature instead of ~330).
+// scalar side, ECDSA.  Each thread owns SV_PREP_BATCH (32) consecutive signatures so that the single
+// Fermat exponentiation mod n is amortised by Montgomery's trick (3 mults + 1/32 of ~330 per signature).
 __global__ void __launch_bounds__(64) k_prep_ecdsa(const u8* msg, const u8* sig, size_t n, sv_work* work) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t base = t * SV_PREP_BATCH;
@@ -112,15 +112,27 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main(sv_work* work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
            const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict, u8* keyok) {
     const size_t keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
-    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    qtab_entry* tab = scratch + tid * 8;
-    // CTA-uniform trip count (lanes past the end redo item 0 and discard the result) so that every thread
-    // reaches every SV_SYNC() of the barrier-synchronised build variant
-    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += stride) {
-        size_t i = base + threadIdx.x;
-        bool active = i < n;
-        size_t j = active ? i : 0;
+    const unsigned G = gridDim.x, B = blockDim.x;
+    const size_t T = (size_t)G * B;
+    qtab_entry* tab = scratch + ((size_t)blockIdx.x * B + threadIdx.x) * 8;
+    // Interleaved item mapping: in round k, thread t of CTA c takes item k*T + t*G + c.  A partial last round then
+    // keeps the first few WARPS of EVERY CTA busy (instead of all warps of the first few CTAs), so its work is spread
+    // over all SMs and the idle warps simply leave; the re-convergence barrier counts only the warps taking part.
+    const size_t r = (size_t)threadIdx.x * G + blockIdx.x;
+    for (size_t base = 0; base < n; base += T) {
+        const size_t rem = n - base;
+        unsigned act = B;
+        if (rem < T) act = (rem > blockIdx.x) ? (unsigned)(((rem - blockIdx.x + G - 1) / G) < B ? ((rem - blockIdx.x + G - 1) / G) : B) : 0u;
+        const unsigned part = (act + 31u) & ~31u;  // whole warps
+#ifdef SV_MAIN_SYNC
+        __syncthreads();  // everybody is done with the previous round's barriers
+        if (threadIdx.x == 0) sv_sync_threads = part;
+        __syncthreads();
+#endif
+        if (threadIdx.x >= part) return;  // only possible in the last round
+        const size_t i = base + r;
+        const bool active = r < rem;
+        const size_t j = active ? i : 0;  // idle lanes of a participating warp: read-only aliases of item 0
         const sv_work* w = active ? (work + i) : &g_idle_work;
         if (KIND == SV_KIND_SCHNORR) {
             // park R in the work record; k_final_schnorr turns it into a verdict (batched inversion)

@@ -1,6 +1,6 @@
 // verify.cuh — one signature verification, split the way the engine's kernels run it:
 //
-//   scalar side  (K_prep) : parse/range-check (r,s), s^-1 (amortised over a small batch with
+//   scalar side  (K_prep) : parse/range-check (r,s), s^-1 (amortised over a batch of 32 with
 //                           Montgomery's trick), u1 = m/s, u2 = r/s, GLV split of u2, window
 //                           recoding  ->  128-byte sv_work record
 //   curve side   (K_main) : key decode (33-byte compressed / 64-byte x|y / 32-byte x-only),
@@ -158,7 +158,7 @@ SV_HD void schnorr_prep(sv_work& w, const u8* sig64, const u8* xonly32, const u8
 }
 
 // Montgomery's trick: invert n (<= SV_PREP_BATCH) non-zero scalars with ONE exponentiation.
-#define SV_PREP_BATCH 16
+#define SV_PREP_BATCH 32
 SV_HD void sc_batch_inverse(sc* v, int n) {
     sc pre[SV_PREP_BATCH];
     sc acc;
