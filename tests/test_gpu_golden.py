@@ -310,3 +310,23 @@ def test_htlc_loop_device_side_bip143(engine, ref, cln):
     assert np.array_equal(got.astype(bool), ok)
     got33 = engine.check_tx_sigs(0, txs, blob, np.tile(pub33, (n, 1)), sig)
     assert np.array_equal(got33, got)
+
+
+def test_host_api_chunking_and_pipelining(engine):
+    """sv_verify_host above its internal chunk size (2^21) and with slice pipelining: 2.2 M synthesised signatures
+    copied to (pageable) host memory, a few corrupted, verified through the host-buffer API."""
+    import torch
+    n = 2_200_000
+    msg = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    key = torch.empty((n, 33), dtype=torch.uint8, device="cuda")
+    sig = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    engine.synth_device(0, 4242, n, msg.data_ptr(), key.data_ptr(), sig.data_ptr())
+    engine.sync()
+    m, k, s = msg.cpu().numpy(), key.cpu().numpy(), sig.cpu().numpy()
+    bad = np.array([0, 1, 151551, 151552, 757759, 757760, 2097151, 2097152, 2097153, n - 1])
+    m[bad, 9] ^= 0x40
+    got = engine.verify(0, m, k, s)
+    want = np.ones(n, np.uint8)
+    want[bad] = 0
+    assert np.array_equal(got, want)
