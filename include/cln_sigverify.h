@@ -91,6 +91,13 @@ int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_l
 int sv_verify_gossip_host(sv_ctx *ctx, const uint8_t *blob, size_t blob_len, const uint64_t *msg_off,
                           const uint32_t *msg_len, size_t n_msgs, const uint8_t *cu_signers33, int *status);
 
+/* ---- n ECDSA signatures by ONE key (every HTLC signature of a commitment_signed is made
+ *      with remote_htlckey, channeld/channeld.c:2154,2215-2232).  The key is decoded and its multiples table built once;
+ *      each verification skips the per-signature square root and table build.  kind: SV_KIND_ECDSA33 or _XY; key is
+ *      ONE key of that kind. ---- */
+int sv_verify_samekey_host(sv_ctx *ctx, int kind, const uint8_t *key, const uint8_t *msg32, const uint8_t *sig64,
+                           size_t n, uint8_t *verdicts);
+
 /* ---- check_tx_sig with the BIP143 sighash computed ON THE DEVICE.  Replaces, for the one-input
  *      one-output commitment-HTLC transactions of channeld/channeld.c:2215-2232 (shape: common/htlc_tx.c:10-69),
  *      bitcoin_tx_hash_for_sig (bitcoin/signature.c:120-151) -> wally_tx_get_btc_signature_hash ->

@@ -113,16 +113,18 @@ bool pubkey_from_der(const u8 *der, size_t len, struct pubkey *key) {
 void check_tx_sigs_batch(const struct sha256_double *hashes, const struct bitcoin_signature *sigs,
                          const struct pubkey *key, size_t n, bool *ok) {
     if (n == 0) return;
-    u8 *buf = (u8 *)malloc(n * (32 + 64 + 64 + 1));
+    u8 *buf = (u8 *)malloc(n * (32 + 64 + 1));
     if (!buf) die("malloc", -3);
-    u8 *msg = buf, *xy = buf + 32 * n, *sig = xy + 64 * n, *v = sig + 64 * n;
+    u8 xy[64];
+    u8 *msg = buf, *sig = buf + 32 * n, *v = sig + 64 * n;
+    pubkey_to_xy(xy, &key->pubkey);
     for (size_t i = 0; i < n; i++) {
         memcpy(msg + 32 * i, hashes[i].sha.u.u8, 32);
-        pubkey_to_xy(xy + 64 * i, &key->pubkey);
         sig_to_wire(sig + 64 * i, &sigs[i].s);
     }
-    int rc = sv_verify_host(ctx(), SV_KIND_ECDSA_XY, msg, xy, sig, n, v);
-    if (rc != SV_OK) die("sv_verify_host", rc);
+    /* one key for the whole loop: its multiples table is built once on the device */
+    int rc = sv_verify_samekey_host(ctx(), SV_KIND_ECDSA_XY, xy, msg, sig, n, v);
+    if (rc != SV_OK) die("sv_verify_samekey_host", rc);
     for (size_t i = 0; i < n; i++) ok[i] = v[i] == 1;
     free(buf);
 }

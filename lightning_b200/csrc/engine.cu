@@ -153,6 +153,39 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     }
 }
 
+// ---- one key, many signatures (N3): build the key's table once, then a ladder-only curve kernel --------------
+__global__ void k_sharedkey_build(int kind, const u8* key, sv_shared_key* out) {
+#ifdef SV_MAIN_SYNC
+    if (threadIdx.x == 0) sv_sync_threads = blockDim.x;
+    __syncthreads();
+#endif
+    sharedkey_build(out, kind, key);  // all 32 lanes compute the same values and store to the same addresses
+}
+__global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
+    k_main_shared(const sv_work* work, const u8* __restrict__ sig, size_t n, const ge_mem* __restrict__ gtab,
+                  const sv_shared_key* sk, u8* __restrict__ verdict) {
+    const unsigned G = gridDim.x, B = blockDim.x;
+    const size_t T = (size_t)G * B;
+    const size_t r = (size_t)threadIdx.x * G + blockIdx.x;
+    for (size_t base = 0; base < n; base += T) {
+        const size_t rem = n - base;
+        unsigned act = B;
+        if (rem < T) act = (rem > blockIdx.x) ? (unsigned)(((rem - blockIdx.x + G - 1) / G) < B ? ((rem - blockIdx.x + G - 1) / G) : B) : 0u;
+        const unsigned part = (act + 31u) & ~31u;
+#ifdef SV_MAIN_SYNC
+        __syncthreads();
+        if (threadIdx.x == 0) sv_sync_threads = part;
+        __syncthreads();
+#endif
+        if (threadIdx.x >= part) return;
+        const size_t i = base + r;
+        const bool active = r < rem;
+        const sv_work* w = active ? (work + i) : &g_idle_work;
+        u32 v = verify_curve_side_shared(w, sig + 64 * (active ? i : 0), gtab, sk);
+        if (active) verdict[i] = (u8)v;
+    }
+}
+
 // ---- device-side BIP143: one thread per transaction input -> msg32 ----------------------
 __global__ void __launch_bounds__(128) k_bip143(const sv_tx_item* txs, const u8* blob, size_t n, u8* msg32, u8* okout) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -943,6 +976,38 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
     cudaFree(d_moff); cudaFree(d_mlen); cudaFree(d_base); cudaFree(d_status); cudaFree(d_signers); cudaFree(d_keyok);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "gossip ingest", ce);
+    return SV_OK;
+}
+
+// n ECDSA signatures by ONE key (channeld's HTLC loop): table of the key built once, ladder-only kernel
+extern "C" int sv_verify_samekey_host(sv_ctx* ctx, int kind, const uint8_t* key, const uint8_t* msg32, const uint8_t* sig64,
+                                      size_t n, uint8_t* verdicts) {
+    size_t ks = sv_key_size(kind);
+    if (!ctx || ks == 0 || kind == SV_KIND_SCHNORR || (n && (!key || !msg32 || !sig64 || !verdicts))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    rc = ensure_work(ctx, n);
+    if (rc) return rc;
+    sv_shared_key* d_sk = nullptr;
+    CK(cudaMalloc(&d_sk, sizeof(sv_shared_key)));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_key, key, ks, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_msg, msg32, 32 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_sig, sig64, 64 * n, cudaMemcpyHostToDevice, st));
+    k_sharedkey_build<<<1, 32, 0, st>>>(kind, ctx->d_key, d_sk);
+    size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
+    k_prep_ecdsa<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_msg, ctx->d_sig, n, ctx->d_work);
+    size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
+    unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
+    k_main_shared<<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, ctx->d_sig, n, ctx->d_gtab, d_sk, ctx->d_verdict);
+    ctx->launches += 3;
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(verdicts, ctx->d_verdict, n, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d_sk);
+    if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "sv_verify_samekey_host", ce);
     return SV_OK;
 }
 

@@ -287,9 +287,8 @@ SV_HD void qtable_fetch(ge& p, const qtab_entry* tab, u32 v, u32 sneg, bool lam)
 }
 
 // R = u1*G + u2*Q in true Jacobian coordinates.
-SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* gtab, qtab_entry* tab) {
-    fe zc;
-    qtable_build(tab, zc, Q);
+// R = u1*G + u2*Q given a ready odd-multiples table of Q (common Z = zc)
+SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qtab_entry* tab, const fe& zc) {
     const u32* m1 = w->k1;
     const u32* m2 = w->k2;
     u32 t1 = m1[4], t2 = m2[4];
@@ -340,6 +339,41 @@ SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* g
             gej_add_ge(R, R, p);
         }
     }
+}
+
+SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* gtab, qtab_entry* tab) {
+    fe zc;
+    qtable_build(tab, zc, Q);
+    ecmult_ladder(R, w, gtab, tab, zc);
+}
+
+SV_HD u32 ecdsa_final(const gej& R, const u8* sig64, u32 flags);
+
+// ---- one key, many signatures (channeld's HTLC loop): the key is decoded and its
+// odd-multiples table built ONCE (k_sharedkey_build); every verification then skips the square root (267 field mults)
+// and the table build (132): ~18 % less work per signature.
+struct alignas(16) sv_shared_key {
+    qtab_entry tab[8];
+    u32 zc[8];
+    u32 ok, pad[3];
+};
+SV_HD void sharedkey_build(sv_shared_key* out, int kind, const u8* key) {
+    ge Q;
+    bool ok = key_decode(Q, kind, key);
+    fe zc;
+    qtable_build(out->tab, zc, Q);
+    fe_to_words(out->zc, zc);
+    out->ok = ok ? 1u : 0u;
+}
+SV_HD u32 verify_curve_side_shared(const sv_work* w, const u8* sig64, const ge_mem* gtab, const sv_shared_key* sk) {
+    u32 flags = w->flags;
+    bool ok = (flags & SV_WF_VALID) != 0 && sk->ok != 0;
+    fe zc;
+    fe_from_words(zc, sk->zc);
+    gej R;
+    ecmult_ladder(R, w, gtab, sk->tab, zc);
+    u32 v = ecdsa_final(R, sig64, flags);
+    return ok ? v : 0u;
 }
 
 // final comparison, ECDSA: x(R) mod n == r without leaving Jacobian coordinates

@@ -59,6 +59,7 @@ def load_library():
     lib.sv_verify_device.argtypes = [vp, i, vp, vp, vp, sz, vp, vp, vp]
     lib.sv_verify_gossip_host.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
     lib.sv_verify_tx_host.argtypes = [vp, i, vp, vp, sz, vp, vp, sz, vp, vp]
+    lib.sv_verify_samekey_host.argtypes = [vp, i, vp, vp, vp, sz, vp]
     lib.sv_sync.argtypes = [vp, vp]
     lib.sv_get_stream.argtypes = [vp]
     lib.sv_set_profiling.argtypes = [vp, i]
@@ -174,6 +175,18 @@ class SigVerifier:
                                                    sg.ctypes.data if sg is not None else None, status.ctypes.data),
                     "sv_verify_gossip_host")
         return status[:n]
+
+    def verify_samekey(self, kind, key, msg32, sig64):
+        """n ECDSA signatures by ONE key (channeld's HTLC loop): the key's table is built once on the device."""
+        msg32 = _u8(msg32, 32)
+        sig64 = _u8(sig64, 64)
+        k = np.ascontiguousarray(key, dtype=np.uint8).reshape(-1)
+        assert k.size == KEY_SIZE[kind]
+        n = msg32.shape[0]
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self.lib.sv_verify_samekey_host(self._ctx, kind, k.ctypes.data, msg32.ctypes.data, sig64.ctypes.data, n,
+                                                    out.ctypes.data), "sv_verify_samekey_host")
+        return out[:n]
 
     def check_tx_sigs(self, kind, txs, scripts, key, sig64, want_sighash=False):
         """check_tx_sig (bitcoin/signature.c:194) for n one-input one-output transactions with the BIP143 sighash

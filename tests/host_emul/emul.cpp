@@ -126,6 +126,30 @@ void emul_bip340_challenge(const u8* r32, const u8* px32, const u8* msg32, u8* o
     sha256_bip340_challenge(out32, r32, px32, msg32);
 }
 
+// same-key path: table built once (sharedkey_build), ladder-only verification
+void emul_verify_samekey(int kind, const u8* key, const u8* msg, const u8* sig, size_t n, u8* out) {
+    build_gtable_fast();
+    sv_shared_key sk;
+    sharedkey_build(&sk, kind, key);
+    for (size_t base = 0; base < n; base += SV_PREP_BATCH) {
+        int cnt = (int)((n - base < SV_PREP_BATCH) ? (n - base) : SV_PREP_BATCH);
+        sc r[SV_PREP_BATCH], m[SV_PREP_BATCH], sv[SV_PREP_BATCH];
+        bool ok[SV_PREP_BATCH];
+        for (int j = 0; j < cnt; j++) {
+            sc s;
+            ok[j] = ecdsa_parse(r[j], s, m[j], sig + 64 * (base + j), msg + 32 * (base + j), nullptr);
+            if (!ok[j]) { memset(s.v, 0, 32); s.v[0] = 1; }
+            sv[j] = s;
+        }
+        sc_batch_inverse(sv, cnt);
+        for (int j = 0; j < cnt; j++) {
+            sv_work w;
+            ecdsa_finish_prep(w, ok[j], r[j], m[j], sv[j]);
+            out[base + j] = (u8)verify_curve_side_shared(&w, sig + 64 * (base + j), g_table.data(), &sk);
+        }
+    }
+}
+
 int emul_bip143(const void* tx_item, const u8* blob, u8* out32) {
     sv_tx_item t;
     memcpy(&t, tx_item, sizeof t);

@@ -330,3 +330,23 @@ def test_host_api_chunking_and_pipelining(engine):
     want = np.ones(n, np.uint8)
     want[bad] = 0
     assert np.array_equal(got, want)
+
+
+def test_samekey_batch(engine, ref):
+    """Row N3 on the GPU: 483 (and ragged counts of) signatures by one key through sv_verify_samekey_host."""
+    rng = np.random.default_rng(8)
+    sk = rng.integers(1, 256, size=32, dtype=np.uint8)
+    pub33, pubxy = np.zeros(33, np.uint8), np.zeros(64, np.uint8)
+    assert ref.ref_pubkey_create(P(sk), P(pub33), P(pubxy))
+    for n in (1, 31, 33, 483, 5000):
+        msg = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        sig = np.zeros((n, 64), np.uint8)
+        for i in range(n):
+            assert ref.ref_ecdsa_sign(P(sk), P(msg[i]), P(sig[i]))
+        for i in range(0, n, 7):
+            msg[i, i % 32] ^= 2
+        want = util.ref_verify(ref, 0, msg, np.tile(pub33, (n, 1)), sig)
+        assert np.array_equal(engine.verify_samekey(0, pub33, msg, sig), want), n
+        assert np.array_equal(engine.verify_samekey(1, pubxy, msg, sig), want), n
+    bad = pub33.copy(); bad[5] ^= 1  # very likely not a curve point, certainly not the signer
+    assert not engine.verify_samekey(0, bad, msg, sig).any()

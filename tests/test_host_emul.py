@@ -188,3 +188,26 @@ def test_device_bip143_preimage_vs_libwally(emul, cln):
         out = np.zeros(32, np.uint8)
         assert emul.emul_bip143(ctypes.byref(txs[i]), P(buf), P(out)) == 1
         assert np.array_equal(out, util.cln_sighash(cln, txs[i], blob)), (i, txs[i].sighash_type)
+
+
+def test_samekey_path(emul, ref):
+    """Row N3: one key, many signatures — table built once, ladder-only verification (host build of the kernel code)."""
+    rng = np.random.default_rng(6)
+    n = 90
+    sk = rng.integers(1, 256, size=32, dtype=np.uint8)
+    pub33, pubxy = np.zeros(33, np.uint8), np.zeros(64, np.uint8)
+    assert ref.ref_pubkey_create(P(sk), P(pub33), P(pubxy))
+    msg = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sig = np.zeros((n, 64), np.uint8)
+    for i in range(n):
+        assert ref.ref_ecdsa_sign(P(sk), P(msg[i]), P(sig[i]))
+    msg[5, 0] ^= 1; sig[17, 40] ^= 1; sig[33, 32:] = 255; sig[60, :32] = 0
+    want = util.ref_verify(ref, 0, msg, np.tile(pub33, (n, 1)), sig)
+    for kind, key in ((0, pub33), (1, pubxy)):
+        out = np.zeros(n, np.uint8)
+        emul.emul_verify_samekey(kind, P(key), P(msg), P(sig), ctypes.c_size_t(n), P(out))
+        assert np.array_equal(out, want), kind
+    bad = pub33.copy(); bad[0] = 5
+    out = np.ones(n, np.uint8)
+    emul.emul_verify_samekey(0, P(bad), P(msg), P(sig), ctypes.c_size_t(n), P(out))
+    assert not out.any()
