@@ -125,9 +125,7 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
         if (rem < T) act = (rem > blockIdx.x) ? (unsigned)(((rem - blockIdx.x + G - 1) / G) < B ? ((rem - blockIdx.x + G - 1) / G) : B) : 0u;
         const unsigned part = (act + 31u) & ~31u;  // whole warps
 #ifdef SV_MAIN_SYNC
-        __syncthreads();  // everybody is done with the previous round's barriers
-        if (threadIdx.x == 0) sv_sync_threads = part;
-        __syncthreads();
+        __syncthreads();  // all warps are out of the previous round's counted barriers before the count may change
 #endif
         if (threadIdx.x >= part) return;  // only possible in the last round
         const size_t i = base + r;
@@ -140,11 +138,11 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
             ge Q;
             ok = key_decode(Q, KIND, key + keylen * j) && ok;
             gej R;
-            ecmult_uniform(R, w, Q, gtab, tab);
+            ecmult_uniform(R, w, Q, gtab, tab, part);
             if (active) schnorr_park(reinterpret_cast<sv_jac*>(work + i), R, ok);
         } else {
             bool kd;
-            u32 v = verify_curve_side(KIND, w, key + keylen * j, sig + 64 * j, gtab, tab, &kd);
+            u32 v = verify_curve_side(KIND, w, key + keylen * j, sig + 64 * j, gtab, tab, &kd, part);
             if (active) {
                 verdict[i] = (u8)v;
                 if (keyok) keyok[i] = kd ? 1 : 0;  // gossip ingest distinguishes "undecodable key" (malformed message)
@@ -155,11 +153,7 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
 
 // ---- one key, many signatures (N3): build the key's table once, then a ladder-only curve kernel --------------
 __global__ void k_sharedkey_build(int kind, const u8* key, sv_shared_key* out) {
-#ifdef SV_MAIN_SYNC
-    if (threadIdx.x == 0) sv_sync_threads = blockDim.x;
-    __syncthreads();
-#endif
-    sharedkey_build(out, kind, key);  // all 32 lanes compute the same values and store to the same addresses
+    sharedkey_build(out, kind, key, blockDim.x);  // all 32 lanes compute the same values and store to the same addresses
 }
 __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main_shared(const sv_work* work, const u8* __restrict__ sig, size_t n, const ge_mem* __restrict__ gtab,
@@ -174,14 +168,12 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
         const unsigned part = (act + 31u) & ~31u;
 #ifdef SV_MAIN_SYNC
         __syncthreads();
-        if (threadIdx.x == 0) sv_sync_threads = part;
-        __syncthreads();
 #endif
         if (threadIdx.x >= part) return;
         const size_t i = base + r;
         const bool active = r < rem;
         const sv_work* w = active ? (work + i) : &g_idle_work;
-        u32 v = verify_curve_side_shared(w, sig + 64 * (active ? i : 0), gtab, sk);
+        u32 v = verify_curve_side_shared(w, sig + 64 * (active ? i : 0), gtab, sk, part);
         if (active) verdict[i] = (u8)v;
     }
 }

@@ -214,7 +214,7 @@ SV_HD u32 window4(const u32* mag, int i) {
 
 // Build the effective-affine table of {1,3,...,15}*Q in `tab` (x,y valid on return) and return
 // the common Z of the table in true curve coordinates (zc).  124 field mul/sqr.
-SV_HD void qtable_build(qtab_entry* tab, fe& zc, const ge& Q) {
+SV_HD void qtable_build(qtab_entry* tab, fe& zc, const ge& Q, unsigned sync_threads = 0) {
     gej D, acc;
     gej_set_ge(D, Q);
     gej_double(D, D);  // 2Q = (Xd, Yd, Zd);  on the curve scaled by c = Zd it is the affine point (Xd, Yd)
@@ -234,7 +234,7 @@ SV_HD void qtable_build(qtab_entry* tab, fe& zc, const ge& Q) {
 #endif
     for (int k = 1; k < 8; k++) {
         fe h;
-        SV_SYNC();
+        SV_SYNC(sync_threads);
         gej_add_ge(acc, acc, d_aff, &h);  // (2k+1)Q ; never exceptional for a point of prime order > 15
         fe_to_words(tab[k].x, acc.x);
         fe_to_words(tab[k].y, acc.y);
@@ -288,7 +288,8 @@ SV_HD void qtable_fetch(ge& p, const qtab_entry* tab, u32 v, u32 sneg, bool lam)
 
 // R = u1*G + u2*Q in true Jacobian coordinates.
 // R = u1*G + u2*Q given a ready odd-multiples table of Q (common Z = zc)
-SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qtab_entry* tab, const fe& zc) {
+SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qtab_entry* tab, const fe& zc,
+                         unsigned sync_threads = 0) {
     const u32* m1 = w->k1;
     const u32* m2 = w->k2;
     u32 t1 = m1[4], t2 = m2[4];
@@ -310,7 +311,7 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
 #pragma unroll 1
 #endif
         for (int j = 0; j < 4; j++) {
-            SV_SYNC();
+            SV_SYNC(sync_threads);
             gej_double(R, R);
         }
 #if SV_DEVICE_CODE
@@ -318,7 +319,7 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
 #endif
         for (int half = 0; half < 2; half++) {
             u32 v = half ? window4(m2, i) : window4(m1, i);
-            SV_SYNC();
+            SV_SYNC(sync_threads);
             qtable_fetch(p, tab, v, half ? s2 : s1, half != 0);
             gej_add_ge(R, R, p);
         }
@@ -331,7 +332,7 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
 #endif
     for (int row = 0; row < 16; row++) {
         int d = w->gd[row];
-        SV_SYNC();
+        SV_SYNC(sync_threads);
         if (d != 0) {
             u32 a = (u32)(d < 0 ? -d : d);
             ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
@@ -341,10 +342,11 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
     }
 }
 
-SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* gtab, qtab_entry* tab) {
+SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* gtab, qtab_entry* tab,
+                          unsigned sync_threads = 0) {
     fe zc;
-    qtable_build(tab, zc, Q);
-    ecmult_ladder(R, w, gtab, tab, zc);
+    qtable_build(tab, zc, Q, sync_threads);
+    ecmult_ladder(R, w, gtab, tab, zc, sync_threads);
 }
 
 SV_HD u32 ecdsa_final(const gej& R, const u8* sig64, u32 flags);
@@ -357,21 +359,22 @@ struct alignas(16) sv_shared_key {
     u32 zc[8];
     u32 ok, pad[3];
 };
-SV_HD void sharedkey_build(sv_shared_key* out, int kind, const u8* key) {
+SV_HD void sharedkey_build(sv_shared_key* out, int kind, const u8* key, unsigned sync_threads = 0) {
     ge Q;
     bool ok = key_decode(Q, kind, key);
     fe zc;
-    qtable_build(out->tab, zc, Q);
+    qtable_build(out->tab, zc, Q, sync_threads);
     fe_to_words(out->zc, zc);
     out->ok = ok ? 1u : 0u;
 }
-SV_HD u32 verify_curve_side_shared(const sv_work* w, const u8* sig64, const ge_mem* gtab, const sv_shared_key* sk) {
+SV_HD u32 verify_curve_side_shared(const sv_work* w, const u8* sig64, const ge_mem* gtab, const sv_shared_key* sk,
+                                   unsigned sync_threads = 0) {
     u32 flags = w->flags;
     bool ok = (flags & SV_WF_VALID) != 0 && sk->ok != 0;
     fe zc;
     fe_from_words(zc, sk->zc);
     gej R;
-    ecmult_ladder(R, w, gtab, sk->tab, zc);
+    ecmult_ladder(R, w, gtab, sk->tab, zc, sync_threads);
     u32 v = ecdsa_final(R, sig64, flags);
     return ok ? v : 0u;
 }
@@ -465,7 +468,7 @@ SV_HD void schnorr_final_batch(u8* verdict, const sv_jac* jac, const u8* sig64, 
 
 // whole curve side for one item
 SV_HD u32 verify_curve_side(int kind, const sv_work* w, const u8* key, const u8* sig64, const ge_mem* gtab,
-                            qtab_entry* tab, bool* key_ok = nullptr) {
+                            qtab_entry* tab, bool* key_ok = nullptr, unsigned sync_threads = 0) {
     u32 flags = w->flags;
     bool ok = (flags & SV_WF_VALID) != 0;  // an invalid record carries harmless dummy scalars (k1 = k2 = 1, u1 = 0)
     ge Q;
@@ -473,7 +476,7 @@ SV_HD u32 verify_curve_side(int kind, const sv_work* w, const u8* key, const u8*
     if (key_ok) *key_ok = kd;
     ok = kd && ok;
     gej R;
-    ecmult_uniform(R, w, Q, gtab, tab);
+    ecmult_uniform(R, w, Q, gtab, tab, sync_threads);
     u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);
     return ok ? v : 0u;
 }
