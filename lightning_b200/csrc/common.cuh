@@ -44,7 +44,11 @@
 // The last, partial round of k_main runs with fewer warps per CTA, so the re-convergence barrier is a COUNTED named
 // barrier: `n` = number of threads (whole warps) of this CTA taking part in the current round, carried in a register.
 // No memory clobber: the barrier only re-aligns program counters, the threads exchange no data.
+#ifdef SV_BAR_PLAIN
+#define SV_SYNC(n) __syncthreads()
+#else
 #define SV_SYNC(n) asm volatile("bar.sync 1, %0;" ::"r"(n))
+#endif
 #else
 #define SV_SYNC(n) ((void)(n))
 #endif

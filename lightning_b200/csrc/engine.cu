@@ -118,11 +118,17 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     // Interleaved item mapping: in round k, thread t of CTA c takes item k*T + t*G + c.  A partial last round then
     // keeps the first few WARPS of EVERY CTA busy (instead of all warps of the first few CTAs), so its work is spread
     // over all SMs and the idle warps simply leave; the re-convergence barrier counts only the warps taking part.
+#ifdef SV_MAP_CONTIG
+    const size_t r = (size_t)blockIdx.x * B + threadIdx.x;
+#else
     const size_t r = (size_t)threadIdx.x * G + blockIdx.x;
+#endif
     for (size_t base = 0; base < n; base += T) {
         const size_t rem = n - base;
         unsigned act = B;
+#if !defined(SV_MAP_CONTIG) && !defined(SV_BAR_PLAIN)
         if (rem < T) act = (rem > blockIdx.x) ? (unsigned)(((rem - blockIdx.x + G - 1) / G) < B ? ((rem - blockIdx.x + G - 1) / G) : B) : 0u;
+#endif
         const unsigned part = (act + 31u) & ~31u;  // whole warps
 #ifdef SV_MAIN_SYNC
         __syncthreads();  // all warps are out of the previous round's counted barriers before the count may change
