@@ -41,13 +41,11 @@
 // CTA-wide re-convergence points of the curve-side kernel (only in the SV_MAIN_SYNC build variant, where the
 // field arithmetic is inlined and the warps of a CTA are kept at the same PC to share instruction fetches)
 #if defined(__CUDACC__) && defined(SV_MAIN_SYNC)
-// The last, partial round of k_main runs with fewer warps per CTA, so the re-convergence barrier is a COUNTED named
-// barrier: `n` = number of threads (whole warps) of this CTA taking part in the current round, carried in a register.
-// No memory clobber: the barrier only re-aligns program counters, the threads exchange no data.
-#ifdef SV_BAR_PLAIN
-#define SV_SYNC(n) __syncthreads()
-#else
+#ifdef SV_MAP_INTERLEAVED
+// (variant) the last, partial round runs with fewer warps per CTA: COUNTED named barrier, count in a register
 #define SV_SYNC(n) asm volatile("bar.sync 1, %0;" ::"r"(n))
+#else
+#define SV_SYNC(n) __syncthreads()
 #endif
 #else
 #define SV_SYNC(n) ((void)(n))

@@ -112,31 +112,36 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main(sv_work* work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
            const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict, u8* keyok) {
     const size_t keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
+#ifndef SV_MAP_INTERLEAVED
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    qtab_entry* tab = scratch + tid * 8;
+    // CTA-uniform trip count (lanes past the end redo dummy work and discard the result) so that every thread
+    // reaches every SV_SYNC() of the barrier-synchronised build
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        size_t i = base + threadIdx.x;
+        bool active = i < n;
+        size_t j = active ? i : 0;
+        const unsigned part = 0;
+#else
+    // VARIANT (measured 1.3 % slower at 1 M, profiles/r1_variants.md): interleaved item mapping — in round k thread t of
+    // CTA c takes item k*T + t*G + c, so a partial last round keeps the first warps of EVERY CTA busy, the idle warps
+    // leave, and the re-convergence barrier counts only the warps taking part.
     const unsigned G = gridDim.x, B = blockDim.x;
     const size_t T = (size_t)G * B;
     qtab_entry* tab = scratch + ((size_t)blockIdx.x * B + threadIdx.x) * 8;
-    // Interleaved item mapping: in round k, thread t of CTA c takes item k*T + t*G + c.  A partial last round then
-    // keeps the first few WARPS of EVERY CTA busy (instead of all warps of the first few CTAs), so its work is spread
-    // over all SMs and the idle warps simply leave; the re-convergence barrier counts only the warps taking part.
-#ifdef SV_MAP_CONTIG
-    const size_t r = (size_t)blockIdx.x * B + threadIdx.x;
-#else
     const size_t r = (size_t)threadIdx.x * G + blockIdx.x;
-#endif
     for (size_t base = 0; base < n; base += T) {
         const size_t rem = n - base;
         unsigned act = B;
-#if !defined(SV_MAP_CONTIG) && !defined(SV_BAR_PLAIN)
         if (rem < T) act = (rem > blockIdx.x) ? (unsigned)(((rem - blockIdx.x + G - 1) / G) < B ? ((rem - blockIdx.x + G - 1) / G) : B) : 0u;
-#endif
         const unsigned part = (act + 31u) & ~31u;  // whole warps
-#ifdef SV_MAIN_SYNC
         __syncthreads();  // all warps are out of the previous round's counted barriers before the count may change
-#endif
         if (threadIdx.x >= part) return;  // only possible in the last round
         const size_t i = base + r;
         const bool active = r < rem;
-        const size_t j = active ? i : 0;  // idle lanes of a participating warp: read-only aliases of item 0
+        const size_t j = active ? i : 0;
+#endif
         const sv_work* w = active ? (work + i) : &g_idle_work;
         if (KIND == SV_KIND_SCHNORR) {
             // park R in the work record; k_final_schnorr turns it into a verdict (batched inversion)
@@ -164,22 +169,12 @@ __global__ void k_sharedkey_build(int kind, const u8* key, sv_shared_key* out) {
 __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main_shared(const sv_work* work, const u8* __restrict__ sig, size_t n, const ge_mem* __restrict__ gtab,
                   const sv_shared_key* sk, u8* __restrict__ verdict) {
-    const unsigned G = gridDim.x, B = blockDim.x;
-    const size_t T = (size_t)G * B;
-    const size_t r = (size_t)threadIdx.x * G + blockIdx.x;
-    for (size_t base = 0; base < n; base += T) {
-        const size_t rem = n - base;
-        unsigned act = B;
-        if (rem < T) act = (rem > blockIdx.x) ? (unsigned)(((rem - blockIdx.x + G - 1) / G) < B ? ((rem - blockIdx.x + G - 1) / G) : B) : 0u;
-        const unsigned part = (act + 31u) & ~31u;
-#ifdef SV_MAIN_SYNC
-        __syncthreads();
-#endif
-        if (threadIdx.x >= part) return;
-        const size_t i = base + r;
-        const bool active = r < rem;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        size_t i = base + threadIdx.x;
+        bool active = i < n;
         const sv_work* w = active ? (work + i) : &g_idle_work;
-        u32 v = verify_curve_side_shared(w, sig + 64 * (active ? i : 0), gtab, sk, part);
+        u32 v = verify_curve_side_shared(w, sig + 64 * (active ? i : 0), gtab, sk, blockDim.x);
         if (active) verdict[i] = (u8)v;
     }
 }
