@@ -3,7 +3,8 @@
 // Kernels (SURVEY.md §2.3 naming):
 //   K4  k_gtable_bases / k_gtable_fill   fixed-base comb table d * 2^(16 i) * G, built once per context
 //   K3  k_sha256d                        SHA-256d of message spans (gossip tails, BIP143 preimages)
-//   K1a k_prep_ecdsa                     scalar side of ECDSA (16 signatures per thread, one s^-1 exponentiation)
+//   K1a k_prep_inv + k_prep_finish       scalar side of ECDSA (32 signatures per thread share one s^-1 exponentiation;
+//                                        then one thread per signature: u1, u2, GLV split, recoding)
 //   K2a k_prep_schnorr                   scalar side of BIP-340 (tagged challenge hash, -e, recoding)
 //   K1b/K2b k_main<kind>                 curve side: thread per verification, persistent grid
 //       k_pack_bitmap                    verdict bytes -> 1 bit per verification (ballot)
@@ -59,9 +60,13 @@ __global__ void __launch_bounds__(128) k_sha256d(const u8* data, const u64* off,
     if (i < n) sha256d_bytes(out32 + 32 * i, data + off[i], len[i]);
 }
 
-// scalar side, ECDSA.  Each thread owns SV_PREP_BATCH (32) consecutive signatures so that the single
-// Fermat exponentiation mod n is amortised by Montgomery's trick (3 mults + 1/32 of ~330 per signature).
-__global__ void __launch_bounds__(64) k_prep_ecdsa(const u8* msg, const u8* sig, size_t n, sv_work* work) {
+// scalar side, ECDSA, in two kernels.
+//   k_prep_inv    : each thread owns SV_PREP_BATCH (32) consecutive signatures: range checks and ONE Fermat
+//                   exponentiation mod n amortised by Montgomery's trick (3 mults + 1/32 of ~330 per signature).  Few
+//                   threads, long serial chains: latency bound, so it does nothing else.  Leaves s^-1 and the check
+//                   flags in the (not yet used) work record.
+//   k_prep_finish : one thread per signature: u1 = m/s, u2 = r/s, GLV split, window recoding -> work record.
+__global__ void __launch_bounds__(64) k_prep_inv(const u8* msg, const u8* sig, size_t n, sv_work* work) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t base = t * SV_PREP_BATCH;
     if (base >= n) return;
@@ -84,12 +89,26 @@ __global__ void __launch_bounds__(64) k_prep_ecdsa(const u8* msg, const u8* sig,
     sc_batch_inverse(sv, SV_PREP_BATCH);
 #pragma unroll 1
     for (int j = 0; j < cnt; j++) {
-        sc r, s, m;
-        (void)ecdsa_parse(r, s, m, sig + 64 * (base + j), msg + 32 * (base + j));
-        sv_work w;
-        ecdsa_finish_prep(w, (okmask >> j) & 1u, r, m, sv[j], (parsedmask >> j) & 1u);
-        work[base + j] = w;
+        u32* w = reinterpret_cast<u32*>(work + base + j);
+        fe_to_words(w, *reinterpret_cast<const fe*>(&sv[j]));  // words 0..7: s^-1
+        w[8] = ((okmask >> j) & 1u) | (((parsedmask >> j) & 1u) << 1);
     }
+}
+__global__ void __launch_bounds__(128) k_prep_finish(const u8* msg, const u8* sig, size_t n, sv_work* work) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32* wi = reinterpret_cast<const u32*>(work + i);
+    sc sinv;
+    fe tmp;
+    fe_from_words(tmp, wi);
+#pragma unroll
+    for (int k = 0; k < 8; k++) sinv.v[k] = tmp.v[k];
+    u32 f = wi[8];
+    sc r, s, m;
+    (void)ecdsa_parse(r, s, m, sig + 64 * i, msg + 32 * i);
+    sv_work w;
+    ecdsa_finish_prep(w, (f & 1u) != 0, r, m, sinv, (f & 2u) != 0);
+    work[i] = w;
 }
 
 __global__ void __launch_bounds__(128) k_prep_schnorr(const u8* msg, const u8* key, const u8* sig, size_t n,
@@ -723,7 +742,9 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
         k_prep_schnorr<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_work);
     } else {
         size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
-        k_prep_ecdsa<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_msg, d_sig, n, ctx->d_work);
+        k_prep_inv<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_msg, d_sig, n, ctx->d_work);
+        k_prep_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_sig, n, ctx->d_work);
+        ctx->launches += 1;
     }
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
@@ -991,7 +1012,9 @@ extern "C" int sv_verify_samekey_host(sv_ctx* ctx, int kind, const uint8_t* key,
     CK(cudaMemcpyAsync(ctx->d_sig, sig64, 64 * n, cudaMemcpyHostToDevice, st));
     k_sharedkey_build<<<1, 32, 0, st>>>(kind, ctx->d_key, d_sk);
     size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
-    k_prep_ecdsa<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_msg, ctx->d_sig, n, ctx->d_work);
+    k_prep_inv<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_msg, ctx->d_sig, n, ctx->d_work);
+    k_prep_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_msg, ctx->d_sig, n, ctx->d_work);
+    ctx->launches += 1;
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
     k_main_shared<<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, ctx->d_sig, n, ctx->d_gtab, d_sk, ctx->d_verdict);

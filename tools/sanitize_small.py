@@ -19,3 +19,13 @@ opk = np.zeros(64, np.uint8)
 assert ref.ref_make_opaque_pubkey(util.P(np.ascontiguousarray(w["pub33"][1])), util.P(opk))
 r = lib.check_schnorr_sig(util.P(np.ascontiguousarray(w["msg"][1])), util.P(opk), util.P(np.ascontiguousarray(w["ssig"][1])))
 print("dropin schnorr", r)
+# newer entry points: gossip slicing, BIP143, same-key
+from tests import gossip
+msgs = gossip.load_subset()
+sel = [m for m in msgs if m[:2] == b"\x01\x00"][:20] + [m for m in msgs if m[:2] == b"\x01\x01"][:20] + [b"\x01\x00" + bytes(50)]
+print("gossip", list(eng.verify_gossip(sel))[-3:])
+rng = np.random.default_rng(1)
+txs, blob = util.make_htlc_txs(rng, 40)
+keys = np.tile(w["pubxy"][0], (40, 1))
+print("tx", eng.check_tx_sigs(1, txs, blob, keys, w["sig"][:40]).sum())
+print("samekey", eng.verify_samekey(0, w["pub33"][0], w["msg"][:70], w["sig"][:70]).sum())
