@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(128) k_synth(u64 seed, size_t n, const ge_mem*
 //   5 k_probe_carry_save  IMAD.WIDE.U32 with carry-OUT only + one IADD3.X per product -> MAC/s
 //   6 k_probe_imad32      separate 32-bit IMAD (lo) / IMAD.HI  -> instr/s
 //   7 k_probe_addc        8-long IADD3(.X) carry chains -> adds/s
+//   8 k_probe_dfma        independent FP64 FMA chains -> DFMA/s (the idle FP64 pipe; round-2 idea: DFMA-based products)
 #define PROBE_PROLOGUE u32 t = blockIdx.x * blockDim.x + threadIdx.x
 __global__ void __launch_bounds__(256) k_probe_imad_wide(int iters, u32* sink) {
     PROBE_PROLOGUE;
@@ -550,6 +551,25 @@ __global__ void __launch_bounds__(256) k_probe_imad32(int iters, u32* sink) {
 #pragma unroll
     for (int k = 0; k < 8; k++) s ^= a[k];
     if (s == 0x12345u) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_dfma(int iters, u32* sink) {
+    PROBE_PROLOGUE;
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + (double)(t + k) * 1e-9;
+    double x = 1.0000001 + (double)t * 1e-12, y = 0.9999999;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = fma(a[k], x, y);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == 1234.5) sink[0] = 1;
 }
 __global__ void __launch_bounds__(256) k_probe_addc(int iters, u32* sink) {
     PROBE_PROLOGUE;
@@ -1136,7 +1156,7 @@ extern "C" int sv_synth_device(sv_ctx* ctx, int kind, uint64_t seed, size_t n, v
 }
 
 extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
-    if (!ctx || !ops_per_sec || mode < 0 || mode > 7) return SV_ERR_ARG;
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 8) return SV_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const int iters = (mode == 2 || mode == 3) ? 2000 : 4000;
     const int blocks = ctx->sm_count * 8, threads = 256;
@@ -1154,6 +1174,7 @@ extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
             case 4: k_probe_chain8<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
             case 5: k_probe_carry_save<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
             case 6: k_probe_imad32<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 8: k_probe_dfma<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
             default: k_probe_addc<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
         }
         CK(cudaEventRecord(e1, ctx->stream));
@@ -1166,7 +1187,7 @@ extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     // operations per thread per launch
-    static const double per_iter[8] = {32.0, 32.0, 2.0, 2.0, 32.0, 32.0, 32.0, 64.0};
+    static const double per_iter[9] = {32.0, 32.0, 2.0, 2.0, 32.0, 32.0, 32.0, 64.0, 32.0};
     *ops_per_sec = per_iter[mode] * iters * (double)blocks * threads / (best * 1e-3);
     return SV_OK;
 }

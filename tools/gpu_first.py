@@ -6,7 +6,7 @@ import lightning_b200 as L
 
 eng = L.SigVerifier(0)
 print("info", eng.info())
-names = ["imad_wide MAC/s", "cmad4 MAC/s", "fe_mul/s", "fe_sqr/s", "chain8 MAC/s", "carry_save MAC/s", "imad32 instr/s", "addc adds/s"]
+names = ["imad_wide MAC/s", "cmad4 MAC/s", "fe_mul/s", "fe_sqr/s", "chain8 MAC/s", "carry_save MAC/s", "imad32 instr/s", "addc adds/s", "dfma /s"]
 if "--noprobe" not in sys.argv:
     for mode, name in enumerate(names):
         v = eng.probe(mode)
