@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "lightning_b200", "csrc")
 LIB = os.path.join(ROOT, "lightning_b200", "libcln_sigverify.so")
 EMUL = os.path.join(ROOT, "tests", "host_emul", "libemul.so")
+DAEMON = os.path.join(ROOT, "lightning_b200", "cln_sigverifyd")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -57,6 +58,11 @@ def build_engine(force=False, verbose=False, extra_flags=()):
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    # verifier subdaemon (row N4): plain C, links the engine
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-std=c11", os.path.join(CSRC, "sigverifyd.c"), "-o", DAEMON,
+                        "-L" + os.path.dirname(LIB), "-lcln_sigverify", "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc (sigverifyd.c) failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

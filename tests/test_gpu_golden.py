@@ -350,3 +350,46 @@ def test_samekey_batch(engine, ref):
         assert np.array_equal(engine.verify_samekey(1, pubxy, msg, sig), want), n
     bad = pub33.copy(); bad[5] ^= 1  # very likely not a curve point, certainly not the signer
     assert not engine.verify_samekey(0, bad, msg, sig).any()
+
+
+def test_verifier_subdaemon(ref, tmp_path):
+    """Row N4: one GPU-owning process serving several clients over a unix socket (CLN-style framed requests)."""
+    import socket, struct, subprocess, time
+    from lightning_b200 import build
+    sock_path = str(tmp_path / "sv.sock")
+    proc = subprocess.Popen([build.DAEMON, sock_path, "0"], stderr=subprocess.PIPE)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock_path):
+                break
+            time.sleep(0.1)
+        assert os.path.exists(sock_path), "daemon did not come up"
+        w = util.corrupt(util.make_signed(ref, 900, seed=21), every=6)
+        clients = [socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) for _ in range(3)]
+        for c in clients:
+            c.connect(sock_path)
+        reqs = [(0, "pub33", "sig", slice(0, 300)), (1, "pubxy", "sig", slice(300, 600)), (2, "xonly", "ssig", slice(600, 900))]
+        for c, (kind, k, s, sl) in zip(clients, reqs):  # all three requests in flight before any reply is read
+            body = bytes([kind]) + struct.pack(">I", 300) + w["msg"][sl].tobytes() + w[k][sl].tobytes() + w[s][sl].tobytes()
+            c.sendall(struct.pack(">I", len(body)) + body)
+        for c, (kind, k, s, sl) in zip(clients, reqs):
+            def rd(n):
+                b = b""
+                while len(b) < n:
+                    chunk = c.recv(n - len(b))
+                    assert chunk
+                    b += chunk
+                return b
+            ln = struct.unpack(">I", rd(4))[0]
+            payload = rd(ln)
+            assert struct.unpack(">I", payload[:4])[0] == 300
+            got = np.frombuffer(payload[4:], dtype=np.uint8)
+            want = util.ref_verify(ref, kind, w["msg"][sl], w[k][sl], w[s][sl])
+            assert np.array_equal(got, want), kind
+        clients[0].sendall(struct.pack(">I", 5) + bytes([9]) + struct.pack(">I", 0))  # bad kind: connection dropped
+        assert clients[0].recv(4) == b""
+        for c in clients:
+            c.close()
+    finally:
+        proc.terminate()
+        proc.wait(timeout=10)
