@@ -1,0 +1,45 @@
+"""Measure the BASELINE.json configs that are parity-test cases rather than bench lines (C3 mixed ECDSA+BIP-340,
+C4 gossip replay) on one GPU; one JSON line each.  Verdicts are checked (by construction / against the fixture)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import lightning_b200 as L
+from tests import gossip
+
+eng = L.SigVerifier(0)
+ext = torch.cuda.ExternalStream(eng.stream_handle())
+
+# ---- C3: 1M mixed: 500k ECDSA (33-byte keys) + 500k BIP-340, two kind-segregated sub-batches, one timed region
+n = 500_000
+bufs = {}
+for kind, ks in ((0, 33), (2, 32)):
+    m = torch.empty((n, 32), dtype=torch.uint8, device="cuda"); k = torch.empty((n, ks), dtype=torch.uint8, device="cuda")
+    s = torch.empty((n, 64), dtype=torch.uint8, device="cuda"); v = torch.empty(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    eng.synth_device(kind, 7 + kind, n, m.data_ptr(), k.data_ptr(), s.data_ptr()); eng.sync()
+    bad = torch.arange(0, n, 10, device="cuda"); m[bad, 3] ^= 1
+    torch.cuda.synchronize()
+    bufs[kind] = (m, k, s, v, bad)
+best = 1e9
+for rep in range(4):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for kind in (0, 2):
+        m, k, s, v, _ = bufs[kind]
+        eng.verify_device(kind, m.data_ptr(), k.data_ptr(), s.data_ptr(), n, v.data_ptr())
+    e1.record(ext); eng.sync()
+    if rep: best = min(best, e0.elapsed_time(e1))
+ok = all(int(bufs[k][3].sum().item()) == n - bufs[k][4].numel() for k in (0, 2))
+print(json.dumps({"config": "C3: 1M mixed ECDSA + BIP-340 (two segregated sub-batches)", "verifies_per_s": 2 * n / best * 1e3,
+                  "ms": best, "verdicts_as_constructed": ok}))
+
+# ---- C4: gossip replay: the mainnet fixture subset tiled to ~80k channel_announcements, device-side slicing+hashing
+msgs = gossip.load_subset()
+ca = [m for m in msgs if m[:2] == b"\x01\x00"]; na = [m for m in msgs if m[:2] == b"\x01\x01"]
+tile = (ca * 54)[:80_000] + na * 37
+sigs = 4 * 80_000 + len(na) * 37
+st = eng.verify_gossip(tile)  # warm-up
+t0 = time.perf_counter(); st = eng.verify_gossip(tile); dt = time.perf_counter() - t0
+print(json.dumps({"config": "C4: gossip replay, 80k channel_announcements + %d node_announcements (real mainnet messages, tiled), host blob -> device slicing -> SHA-256d -> verify" % (len(na) * 37),
+                  "messages": len(tile), "signatures": sigs, "e2e_s": dt, "signatures_per_s": sigs / dt, "messages_per_s": len(tile) / dt,
+                  "all_valid": bool((st == 0).all())}))
