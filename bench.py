@@ -214,8 +214,10 @@ def run_engine(args):
     local = env_int("LOCAL_RANK", 0)
     dist = None
     # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # (NCCL writes its debug output, including that banner, to stdout unless told otherwise)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
