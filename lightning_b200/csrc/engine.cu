@@ -634,6 +634,14 @@ struct sv_ctx {
 
 static std::string g_create_err;
 
+// temporary device allocation released on every exit path
+struct dev_tmp {
+    void* p = nullptr;
+    ~dev_tmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 static int fail(sv_ctx* ctx, int code, const char* what, cudaError_t e) {
     char buf[512];
     snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
@@ -978,13 +986,17 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
         CK(cudaMalloc(&ctx->d_len, need * sizeof(u32)));
         ctx->span_cap = need;
     }
-    u64* d_moff = nullptr; u32 *d_mlen = nullptr, *d_base = nullptr; int* d_status = nullptr; u8 *d_signers = nullptr, *d_keyok = nullptr;
-    CK(cudaMalloc(&d_keyok, cap));
-    CK(cudaMalloc(&d_moff, n_msgs * sizeof(u64)));
-    CK(cudaMalloc(&d_mlen, n_msgs * sizeof(u32)));
-    CK(cudaMalloc(&d_base, n_msgs * sizeof(u32)));
-    CK(cudaMalloc(&d_status, n_msgs * sizeof(int)));
-    if (cu_signers33) CK(cudaMalloc(&d_signers, n_msgs * 33));
+    dev_tmp t_moff, t_mlen, t_base, t_status, t_signers, t_keyok;
+    CK(t_keyok.alloc(cap));
+    CK(t_moff.alloc(n_msgs * sizeof(u64)));
+    CK(t_mlen.alloc(n_msgs * sizeof(u32)));
+    CK(t_base.alloc(n_msgs * sizeof(u32)));
+    CK(t_status.alloc(n_msgs * sizeof(int)));
+    if (cu_signers33) CK(t_signers.alloc(n_msgs * 33));
+    u64* d_moff = t_moff.as<u64>();
+    u32 *d_mlen = t_mlen.as<u32>(), *d_base = t_base.as<u32>();
+    int* d_status = t_status.as<int>();
+    u8 *d_signers = t_signers.as<u8>(), *d_keyok = t_keyok.as<u8>();
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(ctx->d_data, blob, blob_len, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_moff, msg_off, n_msgs * sizeof(u64), cudaMemcpyHostToDevice, st));
@@ -1007,7 +1019,6 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
     }
     cudaError_t ce = cudaMemcpyAsync(status, d_status, n_msgs * sizeof(int), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    cudaFree(d_moff); cudaFree(d_mlen); cudaFree(d_base); cudaFree(d_status); cudaFree(d_signers); cudaFree(d_keyok);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "gossip ingest", ce);
     return SV_OK;
@@ -1024,8 +1035,9 @@ extern "C" int sv_verify_samekey_host(sv_ctx* ctx, int kind, const uint8_t* key,
     if (rc) return rc;
     rc = ensure_work(ctx, n);
     if (rc) return rc;
-    sv_shared_key* d_sk = nullptr;
-    CK(cudaMalloc(&d_sk, sizeof(sv_shared_key)));
+    dev_tmp t_sk;
+    CK(t_sk.alloc(sizeof(sv_shared_key)));
+    sv_shared_key* d_sk = t_sk.as<sv_shared_key>();
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(ctx->d_key, key, ks, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_msg, msg32, 32 * n, cudaMemcpyHostToDevice, st));
@@ -1042,7 +1054,6 @@ extern "C" int sv_verify_samekey_host(sv_ctx* ctx, int kind, const uint8_t* key,
     cudaError_t ce = cudaGetLastError();
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(verdicts, ctx->d_verdict, n, cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    cudaFree(d_sk);
     if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "sv_verify_samekey_host", ce);
     return SV_OK;
 }
@@ -1067,10 +1078,11 @@ extern "C" int sv_verify_tx_host(sv_ctx* ctx, int kind, const sv_tx* txs, const 
         CK(cudaMalloc(&ctx->d_data, scripts_len + 1));
         ctx->data_cap = scripts_len + 1;
     }
-    sv_tx_item* d_txs = nullptr;
-    u8* d_ok = nullptr;
-    CK(cudaMalloc(&d_txs, n * sizeof(sv_tx_item)));
-    CK(cudaMalloc(&d_ok, n));
+    dev_tmp t_txs, t_ok;
+    CK(t_txs.alloc(n * sizeof(sv_tx_item)));
+    CK(t_ok.alloc(n));
+    sv_tx_item* d_txs = t_txs.as<sv_tx_item>();
+    u8* d_ok = t_ok.as<u8>();
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(d_txs, txs, n * sizeof(sv_tx_item), cudaMemcpyHostToDevice, st));
     if (scripts_len) CK(cudaMemcpyAsync(ctx->d_data, scripts, scripts_len, cudaMemcpyHostToDevice, st));
@@ -1087,8 +1099,6 @@ extern "C" int sv_verify_tx_host(sv_ctx* ctx, int kind, const sv_tx* txs, const 
         if (ce == cudaSuccess && sighash32_out) ce = cudaMemcpyAsync(sighash32_out, ctx->d_msg, 32 * n, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     }
-    cudaFree(d_txs);
-    cudaFree(d_ok);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "sv_verify_tx_host", ce);
     return SV_OK;
