@@ -20,8 +20,10 @@ DAEMON = os.path.join(ROOT, "lightning_b200", "cln_sigverifyd")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-    # curve-side kernel variant: inlined field arithmetic + CTA-wide re-convergence barriers (see engine.cu)
-    "-DSV_FE_INLINE", "-DSV_MAIN_SYNC",
+    # curve-side kernel variant: inlined field arithmetic + CTA-wide re-convergence barriers (see engine.cu);
+    # in the ladder one barrier every 2 windows (measured: per point op 45.7, per window 46.4, per 2 windows 46.5,
+    # per 4 windows 46.0, per 8 windows 45.4 M verifies/s — profiles/r1_variants.md)
+    "-DSV_FE_INLINE", "-DSV_MAIN_SYNC", "-DSV_SYNC_LEVEL=1", "-DSV_SYNC_WINDOWS=2",
 ]
 
 

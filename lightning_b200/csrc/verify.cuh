@@ -310,8 +310,16 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
 #if SV_DEVICE_CODE
 #pragma unroll 1
 #endif
+#if defined(SV_SYNC_LEVEL) && SV_SYNC_LEVEL < 2
+#ifndef SV_SYNC_WINDOWS
+#define SV_SYNC_WINDOWS 1
+#endif
+        if (i % SV_SYNC_WINDOWS == 0) SV_SYNC(sync_threads);  // one re-convergence point per SV_SYNC_WINDOWS windows
+#endif
         for (int j = 0; j < 4; j++) {
+#if !defined(SV_SYNC_LEVEL) || SV_SYNC_LEVEL >= 2
             SV_SYNC(sync_threads);
+#endif
             gej_double(R, R);
         }
 #if SV_DEVICE_CODE
@@ -319,7 +327,9 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
 #endif
         for (int half = 0; half < 2; half++) {
             u32 v = half ? window4(m2, i) : window4(m1, i);
+#if !defined(SV_SYNC_LEVEL) || SV_SYNC_LEVEL >= 2
             SV_SYNC(sync_threads);
+#endif
             qtable_fetch(p, tab, v, half ? s2 : s1, half != 0);
             gej_add_ge(R, R, p);
         }
