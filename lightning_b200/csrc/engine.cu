@@ -625,6 +625,9 @@ struct sv_ctx {
     u32* d_len;
     size_t span_cap;
     u32* d_sink;
+    // gossip ingest scratch (grow-only)
+    u8* g_buf;
+    size_t g_cap;
     int profiling;
     cudaEvent_t ev[3];  // before prep, between prep and main, after main (profiling mode only)
     unsigned long long launches;
@@ -696,6 +699,8 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     ctx->d_msg = ctx->d_key = ctx->d_sig = ctx->d_verdict = ctx->d_data = nullptr;
     ctx->d_work = nullptr; ctx->d_off = nullptr; ctx->d_len = nullptr;
     ctx->launches = 0;
+    ctx->g_buf = nullptr;
+    ctx->g_cap = 0;
     ctx->profiling = 0;
     ctx->ev[0] = ctx->ev[1] = ctx->ev[2] = nullptr;
     ctx->stream = ctx->copy_stream = nullptr;
@@ -736,7 +741,7 @@ extern "C" void sv_destroy(sv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_gtab); cudaFree(ctx->d_bases); cudaFree(ctx->d_scratch); cudaFree(ctx->d_sink);
     cudaFree(ctx->d_msg); cudaFree(ctx->d_key); cudaFree(ctx->d_sig); cudaFree(ctx->d_verdict);
-    cudaFree(ctx->d_work); cudaFree(ctx->d_data); cudaFree(ctx->d_off); cudaFree(ctx->d_len);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_data); cudaFree(ctx->d_off); cudaFree(ctx->d_len); cudaFree(ctx->g_buf);
     for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; i++) if (ctx->h2d_ev[i]) cudaEventDestroy(ctx->h2d_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -986,17 +991,20 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
         CK(cudaMalloc(&ctx->d_len, need * sizeof(u32)));
         ctx->span_cap = need;
     }
-    dev_tmp t_moff, t_mlen, t_base, t_status, t_signers, t_keyok;
-    CK(t_keyok.alloc(cap));
-    CK(t_moff.alloc(n_msgs * sizeof(u64)));
-    CK(t_mlen.alloc(n_msgs * sizeof(u32)));
-    CK(t_base.alloc(n_msgs * sizeof(u32)));
-    CK(t_status.alloc(n_msgs * sizeof(int)));
-    if (cu_signers33) CK(t_signers.alloc(n_msgs * 33));
-    u64* d_moff = t_moff.as<u64>();
-    u32 *d_mlen = t_mlen.as<u32>(), *d_base = t_base.as<u32>();
-    int* d_status = t_status.as<int>();
-    u8 *d_signers = t_signers.as<u8>(), *d_keyok = t_keyok.as<u8>();
+    // one grow-only slab: [msg_off u64][msg_len u32][item_base u32][status int][signers 33B][keyok 1B per item]
+    size_t need_g = n_msgs * (8 + 4 + 4 + 4 + 33) + cap + 64;
+    if (need_g > ctx->g_cap) {
+        cudaFree(ctx->g_buf); ctx->g_buf = nullptr; ctx->g_cap = 0;
+        CK(cudaMalloc(&ctx->g_buf, need_g));
+        ctx->g_cap = need_g;
+    }
+    u64* d_moff = reinterpret_cast<u64*>(ctx->g_buf);
+    u32* d_mlen = reinterpret_cast<u32*>(d_moff + n_msgs);
+    u32* d_base = d_mlen + n_msgs;
+    int* d_status = reinterpret_cast<int*>(d_base + n_msgs);
+    u8* d_signers = reinterpret_cast<u8*>(d_status + n_msgs);
+    u8* d_keyok = d_signers + 33 * n_msgs;
+    if (!cu_signers33) d_signers = nullptr;
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(ctx->d_data, blob, blob_len, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_moff, msg_off, n_msgs * sizeof(u64), cudaMemcpyHostToDevice, st));
