@@ -138,3 +138,15 @@ def test_synth_generator_is_valid_under_reference(engine, ref):
         b = bits.cpu().numpy().view(np.uint32)
         unpacked = ((b[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(-1)[:n].astype(np.uint8)
         assert np.array_equal(unpacked, got)
+
+
+def test_mutation_differential(engine, ref):
+    """20,000 structured mutations (boundary r/s/x/m values, negated or swapped fields, random flips): GPU vs reference."""
+    from tests import mutations
+    w = util.make_signed(ref, 20000, seed=321)
+    cls = mutations.mutate(w, seed=10)
+    for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ssig")]):
+        want = util.ref_verify(ref, kind, w["msg"], w[k], w[s], threads=8)
+        got = engine.verify(kind, w["msg"], w[k], w[s])
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, (kind, bad[:5], cls[bad[:5]], want[bad[:5]])

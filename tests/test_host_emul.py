@@ -211,3 +211,17 @@ def test_samekey_path(emul, ref):
     out = np.ones(n, np.uint8)
     emul.emul_verify_samekey(0, P(bad), P(msg), P(sig), ctypes.c_size_t(n), P(out))
     assert not out.any()
+
+
+def test_mutation_differential(emul, ref):
+    """~3,000 structured mutations (boundary values of r, s, x, m; swapped/negated fields; random flips) of valid
+    triples: the host build of the kernel code and the reference must agree on every verdict, for all three kinds."""
+    from tests import mutations
+    w = util.make_signed(ref, 3000, seed=123)
+    cls = mutations.mutate(w, seed=9)
+    for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ssig")]):
+        want = util.ref_verify(ref, kind, w["msg"], w[k], w[s], threads=4)
+        got = emul_verify(emul, kind, w["msg"], w[k], w[s])
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, (kind, bad[:5], cls[bad[:5]], want[bad[:5]])
+        assert 100 < want.sum() < 2900
