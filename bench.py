@@ -152,7 +152,9 @@ def run_reference(args):
         lib.ref_make_ecdsa_batch(ctypes.c_uint64(20260922), ctypes.c_size_t(sample), msg.ctypes.data_as(p8),
                                  pub.ctypes.data_as(p8), sig.ctypes.data_as(p8), threads)
     else:
-        raise SystemExit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref missing and no signer in the port"}))
+        # cannot happen while oracle/_ref travels with the snapshot; keep the driver's contract anyway
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsecp_ref.so is missing (the port has no signer)"}))
+        return 0
     for _ in range(args.warmup):
         cpu_verify(lib, kind, msg, pub, sig, threads)
     t0 = time.perf_counter()

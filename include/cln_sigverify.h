@@ -32,7 +32,8 @@
  * verdict buffer untouched; there is NO CPU fallback.  The check_* drop-in wrappers in
  * cln_dropin.h abort() on engine failure, matching CLN's "internal error is fatal" style.
  *
- * Threading: one sv_ctx per thread/process (CLN daemons are single-threaded event loops).
+ * Threading: one sv_ctx per thread/process (CLN daemons are single-threaded event loops).  Calls on one context
+ * share its device scratch (work records, per-thread tables): issue them one at a time, on one stream at a time.
  */
 #ifndef CLN_SIGVERIFY_H
 #define CLN_SIGVERIFY_H
