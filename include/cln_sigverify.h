@@ -138,6 +138,44 @@ int sv_sha256d_host(sv_ctx *ctx, const uint8_t *data, size_t data_len, const uin
 /* pubkey_from_der semantics for a batch: key33[n][33] -> xy64[n][64] (x||y big-endian), ok[n] = 0/1 */
 int sv_pubkey_parse_host(sv_ctx *ctx, const uint8_t *key33, size_t n, uint8_t *xy64, uint8_t *ok);
 
+/* ---- device-side self test of the arithmetic (TEST SUPPORT; model: libsecp256k1 tests.c:3023-3176 field self-tests,
+ *      :2354 scalar tests).  Runs ONE primitive of the engine's inline-PTX arithmetic on caller operands, one GPU thread
+ *      per item: a[n][8], b[n][8] little-endian 32-bit limbs in; out[n][16] limbs out (result in out[0..7]; flags or the
+ *      high half in out[8..15], see the list).  Field results are in the engine's WEAK form (any value < 2^256
+ *      congruent to the residue) unless stated. ---- */
+enum {
+    SV_ST_FE_MUL = 0,        /* a*b mod p */
+    SV_ST_FE_SQR = 1,        /* a^2 */
+    SV_ST_FE_ADD = 2,        /* a+b */
+    SV_ST_FE_SUB = 3,        /* a-b */
+    SV_ST_FE_NEG = 4,        /* -a */
+    SV_ST_FE_NORMALIZE = 5,  /* canonical a; out[8] = (a == 0 mod p), out[9] = (a >= p), out[10] = (a == b mod p) */
+    SV_ST_FE_INV = 6,        /* a^(p-2) */
+    SV_ST_FE_SQRT = 7,       /* a^((p+1)/4); out[8] = 1 iff it squares back to a */
+    SV_ST_FE_MUL3 = 8,
+    SV_ST_FE_MUL8 = 9,
+    SV_ST_FE_MUL_SMALL = 10, /* a * (b[0] & 0xFFFF) */
+    SV_ST_FE_DBL = 11,
+    SV_ST_FE_B32 = 12,       /* a = 32 big-endian bytes (memory order): set_b32 -> get_b32 round trip; out[8] = (value < p) */
+    SV_ST_U256_MUL_WIDE = 13, /* full 512-bit product in out[0..15] */
+    SV_ST_U256_SQR_WIDE = 14,
+    SV_ST_FE_REDUCE512 = 15,  /* (a + b*2^256) mod p */
+    SV_ST_U256_ADD = 16,      /* out[8] = carry */
+    SV_ST_U256_SUB = 17,      /* out[8] = borrow */
+    SV_ST_SC_MUL = 20,        /* a*b mod n (a, b < n), canonical */
+    SV_ST_SC_SQR = 21,
+    SV_ST_SC_ADD = 22,
+    SV_ST_SC_NEGATE = 23,     /* out[8] = is_high(a), out[9] = is_zero(a), out[10] = (a >= n) */
+    SV_ST_SC_INVERSE = 24,
+    SV_ST_SC_REDUCE512 = 25,  /* (a + b*2^256) mod n */
+    SV_ST_SC_SPLIT_LAMBDA = 26, /* r1 -> out[0..7], r2 -> out[8..15] */
+    SV_ST_SC_SET_B32 = 27,    /* a = 32 big-endian bytes: reduced scalar, out[8] = overflow */
+    SV_ST_ECMULT_GEN = 28,    /* a*G through the fixed-base comb table: affine x -> out[0..7], y -> out[8..15]; 0 -> zeros */
+    SV_ST_PREPARE_U2 = 29,    /* b = u2: |k1| -> out[0..4], |k2| -> out[5..9] (sign in bit 159), both odd */
+    SV_ST_PREPARE_U1 = 30     /* a = u1: 16 signed comb digits -> out[0..15] */
+};
+int sv_selftest_host(sv_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, size_t n, uint32_t *out);
+
 /* ---- synthetic workload generator (benchmark / test support; NOT constant time, no secrets):
  *      item i gets secret key and nonce derived from (seed, i); writes msg32, key (per kind) and a
  *      VALID low-S ECDSA / BIP-340 signature to device arrays. ---- */

@@ -23,6 +23,7 @@
 
 #include "../../include/cln_sigverify.h"
 #include "verify.cuh"
+#include "selftest.cuh"
 
 // Build variants of the curve-side kernel (measured on B200, 1 M ECDSA33 verifications, profiles/):
 //   default  SV_FE_INLINE + SV_MAIN_SYNC, 256 threads x 2 CTAs/SM : field arithmetic inlined, the warps of a CTA
@@ -312,6 +313,19 @@ __global__ void __launch_bounds__(128) k_pubkey_parse(const u8* key33, size_t n,
     okout[i] = ok;
 }
 
+// ---- device-side self test of the arithmetic primitives (test support; body in selftest.cuh) -------
+__global__ void __launch_bounds__(128) k_selftest(int op, const u32* __restrict__ a, const u32* __restrict__ b, size_t n,
+                                                  u32* __restrict__ out, const ge_mem* __restrict__ gtab) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 A[8], B[8], R[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { A[k] = a[8 * i + k]; B[k] = b[8 * i + k]; }
+    selftest_item(op, A, B, R, gtab);
+#pragma unroll
+    for (int k = 0; k < 16; k++) out[16 * i + k] = R[k];
+}
+
 // ---- synthetic workload generator ---------------------------------------------------------------
 SV_D void synth_hash(u8 out[32], u64 seed, u64 idx, u32 tag) {
     u8 buf[20];
@@ -323,30 +337,6 @@ SV_D void synth_hash(u8 out[32], u64 seed, u64 idx, u32 tag) {
         out[4 * k] = (u8)(st[k] >> 24); out[4 * k + 1] = (u8)(st[k] >> 16);
         out[4 * k + 2] = (u8)(st[k] >> 8); out[4 * k + 3] = (u8)st[k];
     }
-}
-// k*G (affine, normalised) with the comb table
-SV_D void synth_base_mult(ge& out, const sc& k, const ge_mem* gtab) {
-    sv_work w;
-    sc_prepare_u1(w, k);
-    gej R;
-    R.inf = 1;
-    fe_set_zero(R.x); fe_set_zero(R.y); fe_set_zero(R.z);
-#pragma unroll 1
-    for (int row = 0; row < 16; row++) {
-        int d = w.gd[row];
-        if (d != 0) {
-            ge p;
-            u32 a = (u32)(d < 0 ? -d : d);
-            ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
-            if (d < 0) fe_neg(p.y, p.y);
-            gej_add_ge(R, R, p);
-        }
-    }
-    fe zi;
-    fe_inv(zi, R.z);
-    ge_set_gej_zinv(out, R, zi);
-    fe_normalize(out.x);
-    fe_normalize(out.y);
 }
 template <int KIND>
 __global__ void __launch_bounds__(128) k_synth(u64 seed, size_t n, const ge_mem* gtab, u8* msg, u8* key, u8* sig) {
@@ -366,8 +356,8 @@ __global__ void __launch_bounds__(128) k_synth(u64 seed, size_t n, const ge_mem*
     for (int q = 0; q < 32; q++) msg[32 * i + q] = h[q];
     sc_set_b32(m, h, nullptr);
     ge P, R;
-    synth_base_mult(P, d, gtab);
-    synth_base_mult(R, k, gtab);
+    ecmult_gen_comb(P, d, gtab);
+    ecmult_gen_comb(R, k, gtab);
     if (KIND == SV_KIND_SCHNORR) {
         // BIP-340 signing equation with even-y P and R: s = k + e*d
         if (fe_is_odd(P.y)) sc_negate(d, d);
@@ -1151,6 +1141,26 @@ extern "C" int sv_flush(sv_ctx* ctx, uint8_t* verdicts, size_t capacity) {
         for (size_t j = 0; j < m; j++) verdicts[idx[j]] = out[j];
     }
     ctx->queue.clear();
+    return SV_OK;
+}
+
+// ---- self test (test support) ---------------------------------------------------------------------
+extern "C" int sv_selftest_host(sv_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
+    if (!ctx || op < 0 || op > SV_ST_PREPARE_U1 || (n && (!a || !b || !out))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    CK(cudaSetDevice(ctx->device));
+    dev_tmp ta, tb, to;
+    CK(ta.alloc(n * 32));
+    CK(tb.alloc(n * 32));
+    CK(to.alloc(n * 64));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ta.p, a, n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(tb.p, b, n * 32, cudaMemcpyHostToDevice, st));
+    k_selftest<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(op, ta.as<u32>(), tb.as<u32>(), n, to.as<u32>(), ctx->d_gtab);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, to.p, n * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return SV_OK;
 }
 

@@ -491,6 +491,34 @@ SV_HD u32 verify_curve_side(int kind, const sv_work* w, const u8* key, const u8*
     return ok ? v : 0u;
 }
 
+// k*G (k != 0) as a normalised affine point through the fixed-base comb alone (signer of the synthetic workload generator,
+// ecmult KAT of the self test).  Not constant time.
+SV_HD void ecmult_gen_comb(ge& out, const sc& k, const ge_mem* gtab) {
+    sv_work w;
+    sc_prepare_u1(w, k);
+    gej R;
+    R.inf = 1;
+    fe_set_zero(R.x); fe_set_zero(R.y); fe_set_zero(R.z);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int row = 0; row < 16; row++) {
+        int d = w.gd[row];
+        if (d != 0) {
+            ge p;
+            u32 a = (u32)(d < 0 ? -d : d);
+            ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
+            if (d < 0) fe_neg(p.y, p.y);
+            gej_add_ge(R, R, p);
+        }
+    }
+    fe zi;
+    fe_inv(zi, R.z);
+    ge_set_gej_zinv(out, R, zi);
+    fe_normalize(out.x);
+    fe_normalize(out.y);
+}
+
 // =================================================================================================
 // fixed-base table construction (K4)
 // =================================================================================================

@@ -73,6 +73,7 @@ def load_library():
     lib.sv_sha256d_host.argtypes = [vp, vp, sz, vp, vp, sz, vp]
     lib.sv_pubkey_parse_host.argtypes = [vp, vp, sz, vp, vp]
     lib.sv_synth_device.argtypes = [vp, i, ctypes.c_uint64, sz, vp, vp, vp, vp]
+    lib.sv_selftest_host.argtypes = [vp, i, vp, vp, sz, vp]
     lib.sv_get_info.argtypes = [vp, ctypes.POINTER(SvInfo)]
     lib.sv_probe.argtypes = [vp, i, ctypes.POINTER(ctypes.c_double)]
     lib.sv_probe_imad_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
@@ -220,6 +221,18 @@ class SigVerifier:
         self._check(self.lib.sv_pubkey_parse_host(self._ctx, key33.ctypes.data, n, xy.ctypes.data, ok.ctypes.data),
                     "sv_pubkey_parse_host")
         return xy, ok
+
+    def selftest(self, op, a, b=None):
+        """Run primitive `op` (SV_ST_* of cln_sigverify.h) of the device arithmetic on operands a, b: (n, 8) uint32
+        little-endian limbs each; returns (n, 16) uint32.  Test support."""
+        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 8)
+        b = np.zeros_like(a) if b is None else np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 8)
+        if a.shape != b.shape:
+            raise ValueError("operand shape mismatch")
+        out = np.zeros((a.shape[0], 16), dtype=np.uint32)
+        self._check(self.lib.sv_selftest_host(self._ctx, int(op), a.ctypes.data, b.ctypes.data, a.shape[0], out.ctypes.data),
+                    "sv_selftest_host")
+        return out
 
     # ---- deferral queue --------------------------------------------------------------------
     def enqueue(self, kind, msg32, key, sig64):

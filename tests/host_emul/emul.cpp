@@ -12,6 +12,7 @@
 #include <cstring>
 #include <vector>
 #include "../../lightning_b200/csrc/verify.cuh"
+#include "../../lightning_b200/csrc/selftest.cuh"
 
 static std::vector<ge_mem> g_table;
 static std::vector<ge_mem> g_bases(16);
@@ -158,6 +159,11 @@ int emul_bip143(const void* tx_item, const u8* blob, u8* out32) {
 size_t emul_sizeof_tx_item(void) { return sizeof(sv_tx_item); }
 
 void emul_gtable_build(void) { build_gtable_fast(); }
+
+// the self-test cases of tests/selftest_cases.py against the host forms of the primitives
+void emul_selftest(int op, const u32* a, const u32* b, size_t n, u32* out) {
+    for (size_t i = 0; i < n; i++) selftest_item(op, a + 8 * i, b + 8 * i, out + 16 * i, g_table.data());
+}
 // entry computed the way the device kernel does it (double-and-add + Fermat), for cross-checking
 void emul_gtable_entry_device_algo(u32 e, u32* xy16) {
     build_gtable_fast();
