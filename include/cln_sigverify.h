@@ -86,8 +86,11 @@ int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_l
  *      blob = concatenated raw wire messages (2-byte type included), msg_off/msg_len locate them.  The device finds
  *      the signatures, keys and signed regions itself, hashes (SHA-256d) and verifies.  status[m] = 0 all signatures
  *      good; 1..4 = first bad signature in the reference's order (node_signature_1, node_signature_2,
- *      bitcoin_signature_1, bitcoin_signature_2; node_announcement / channel_update: 1); -1 = not a gossip message or
- *      too short.  channel_update is signed by a node the caller looks up in its gossmap: cu_signers33[m] (33 bytes per
+ *      bitcoin_signature_1, bitcoin_signature_2; node_announcement / channel_update: 1); -1 = not a gossip message,
+ *      shorter than the message's fixed layout (every field of wire/peer_wire.csv:340-377 up to and including the
+ *      variable-length features / addresses arrays must be present, as the generated fromwire_* require), a signature
+ *      with r or s >= n, or an undecodable bitcoin_key.  NOT checked: the TLV stream that may follow a
+ *      node_announcement (node_ann_tlvs) — a caller that consumes those still parses them itself.  channel_update is signed by a node the caller looks up in its gossmap: cu_signers33[m] (33 bytes per
  *      MESSAGE, ignored for other types; NULL if the batch has no channel_update). ---- */
 int sv_verify_gossip_host(sv_ctx *ctx, const uint8_t *blob, size_t blob_len, const uint64_t *msg_off,
                           const uint32_t *msg_len, size_t n_msgs, const uint8_t *cu_signers33, int *status);
@@ -104,13 +107,18 @@ int sv_verify_samekey_host(sv_ctx *ctx, int kind, const uint8_t *key, const uint
  *      bitcoin_tx_hash_for_sig (bitcoin/signature.c:120-151) -> wally_tx_get_btc_signature_hash ->
  *      bip143_signature_hash (libwally tx_io.c:660-765) + check_signed_hash.  The host passes only the fields of the
  *      preimage; scripts live in one blob.  sighash32_out (optional, n x 32) returns the computed sighashes. ---- */
+#define SV_TX_OUTPUTS_SERIALIZED 1u
 typedef struct {
     uint32_t version, locktime, sequence, sighash_type; /* sighash_type: SIGHASH_ALL 1 / NONE 2 / SINGLE 3, | 0x80 ANYONECANPAY */
     uint8_t prev_txid[32];                              /* as serialised in the transaction (internal byte order) */
     uint32_t prev_index;
     uint32_t script_off, script_len;                    /* witness script (scriptCode) inside `scripts` */
     uint32_t out_script_off, out_script_len;            /* scriptPubKey of the single output inside `scripts` */
-    uint32_t pad;
+    uint32_t pad;                                       /* 0; or SV_TX_OUTPUTS_SERIALIZED: the out_script span holds the
+                                                           already-serialised outputs to commit to (amount || CompactSize
+                                                           || script, concatenated; all outputs for SIGHASH_ALL, the one
+                                                           at the input's index for SIGHASH_SINGLE) and output_amount is
+                                                           ignored — multi-output (commitment) transactions */
     uint64_t input_amount, output_amount;               /* satoshi */
 } sv_tx;
 int sv_verify_tx_host(sv_ctx *ctx, int kind, const sv_tx *txs, const uint8_t *scripts, size_t scripts_len,

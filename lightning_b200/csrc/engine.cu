@@ -237,14 +237,23 @@ __global__ void __launch_bounds__(128) k_gossip_slice(const u8* blob, const u64*
             if (len < keys + 4 * 33) st = -1;
         }
     } else if (type == 257) {
+        // signature(64) flen(2) features timestamp(4) node_id(33) rgb_color(3) alias(32) addrlen(2) addresses
+        // (wire/peer_wire.csv:353-362): fromwire_node_announcement fails on any shorter message
         if (len < 68) st = -1;
         else {
             u32 flen = ((u32)p[66] << 8) | p[67];
             keys = 68 + flen + 4;
-            if (len < keys + 33) st = -1;
+            if (len < keys + 33 + 3 + 32 + 2) st = -1;
+            else {
+                u32 alen = ((u32)p[keys + 68] << 8) | p[keys + 69];
+                if (len < keys + 70 + alen) st = -1;
+            }
         }
     } else if (type == 258) {
-        if (len < 66 + 32 + 8 || signers33 == nullptr) st = -1;
+        // signature(64) chain_hash(32) short_channel_id(8) timestamp(4) message_flags(1) channel_flags(1)
+        // cltv_expiry_delta(2) htlc_minimum_msat(8) fee_base_msat(4) fee_proportional_millionths(4)
+        // htlc_maximum_msat(8) = 138 bytes with the type (wire/peer_wire.csv:366-377; htlc_maximum_msat is mandatory)
+        if (len < 138 || signers33 == nullptr) st = -1;
     } else {
         st = -1;
     }

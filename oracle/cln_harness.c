@@ -141,7 +141,11 @@ int cln_sigcheck_node_announcement(const u8 *msg, size_t len) {
     setup();
     if (len < 68) return -1;
     size_t flen = ((size_t)msg[66] << 8) | msg[67], idoff = 68 + flen + 4;
-    if (len < idoff + 33) return -1;
+    /* the generated fromwire_node_announcement (wire/peer_wire.csv:353-362) also pulls rgb_color(3), alias(32),
+     * addrlen(2) and addrlen bytes of addresses: a shorter message fails to parse */
+    if (len < idoff + 33 + 3 + 32 + 2) return -1;
+    size_t alen = ((size_t)msg[idoff + 68] << 8) | msg[idoff + 69];
+    if (len < idoff + 70 + alen) return -1;
     secp256k1_ecdsa_signature sig;
     const u8 *p = msg + 2;
     size_t max = 64;
@@ -157,7 +161,7 @@ int cln_sigcheck_node_announcement(const u8 *msg, size_t len) {
 }
 int cln_sigcheck_channel_update(const u8 *msg, size_t len, const u8 *node_id33) {
     setup();
-    if (len < 66 + 32 + 8) return -1;
+    if (len < 138) return -1; /* fixed layout of wire/peer_wire.csv:366-377 incl. the mandatory htlc_maximum_msat */
     secp256k1_ecdsa_signature sig;
     const u8 *p = msg + 2;
     size_t max = 64;

@@ -237,6 +237,42 @@ def test_config_c1_dropin_vs_cln_own_functions(engine, ref, cln):
     assert list(st) == want
 
 
+def test_gossip_truncated_but_validly_signed_is_malformed(engine, ref, cln):
+    """a message cut short of its fixed layout but SIGNED CORRECTLY over the shortened tail must be status -1
+    (CLN's generated fromwire_* refuse it), not 0.  channel_update needs all 138 bytes (htlc_maximum_msat is mandatory,
+    wire/peer_wire.csv:366-377); node_announcement needs rgb_color, alias, addrlen and addrlen bytes of addresses (:353-362)."""
+    import hashlib
+    rng = np.random.default_rng(44)
+    sk = rng.integers(1, 256, size=32, dtype=np.uint8)
+    pub33, pubxy = np.zeros(33, np.uint8), np.zeros(64, np.uint8)
+    assert ref.ref_pubkey_create(P(sk), P(pub33), P(pubxy))
+
+    def sign_tail(body_after_sig):
+        h = np.frombuffer(hashlib.sha256(hashlib.sha256(body_after_sig).digest()).digest(), dtype=np.uint8).copy()
+        sig = np.zeros(64, np.uint8)
+        assert ref.ref_ecdsa_sign(P(sk), P(h), P(sig))
+        return bytes(sig)
+
+    cu_body = bytes(rng.integers(0, 256, size=72, dtype=np.uint8))  # chain_hash .. htlc_maximum_msat
+    na_fixed = b"\x00\x00" + b"\x00\x00\x00\x07" + bytes(pub33) + b"\x01\x02\x03" + bytes(32)  # flen=0, ts, id, rgb, alias
+    addrs = bytes([1, 127, 0, 0, 1, 0x26, 0x07])
+    na_body = na_fixed + len(addrs).to_bytes(2, "big") + addrs
+    msgs, signers = [], []
+    for cut in (72, 71, 64, 63, 40):  # full, then shorter and shorter channel_updates, each validly signed as cut
+        body = cu_body[:cut]
+        msgs.append(b"\x01\x02" + sign_tail(body) + body)
+    for cut in (len(na_body), len(na_body) - 1, len(na_fixed) + 2, len(na_fixed) + 1, len(na_fixed), len(na_fixed) - 30, 2 + 4 + 33):
+        body = na_body[:cut]
+        msgs.append(b"\x01\x01" + sign_tail(body) + body)
+    sg = np.tile(pub33, (len(msgs), 1))
+    want = []
+    for m in msgs:
+        L = ctypes.c_size_t(len(m))
+        want.append(cln.cln_sigcheck_channel_update(m, L, P(pub33)) if m[:2] == b"\x01\x02" else cln.cln_sigcheck_node_announcement(m, L))
+    assert want == [0, -1, -1, -1, -1, 0, -1, -1, -1, -1, -1, -1], want
+    assert list(engine.verify_gossip(msgs, sg)) == want
+
+
 def test_gossip_device_side_slicing_vs_gossipd(engine, cln):
     """Row N1: raw wire messages in, the DEVICE finds signatures/keys/signed regions (k_gossip_slice), hashes and
     verifies; per-message status must equal what CLN's own gossipd/sigcheck.c returns for the same bytes."""
@@ -261,7 +297,8 @@ def test_gossip_device_side_slicing_vs_gossipd(engine, cln):
                     break
             b[pos] ^= 1 << int(rng.integers(0, 8))
         batch.append(bytes(b))
-    batch += [sel[0][:200], sel[401][:60], b"\x01\x03" + bytes(100), b"\x01", sel[5] + b"\x00" * 7]  # malformed / foreign / padded
+    batch += [sel[0][:200], sel[401][:60], b"\x01\x03" + bytes(100), b"\x01", sel[5] + b"\x00" * 7,  # malformed / foreign / padded
+              sel[601][:137], sel[601][:130], sel[402][:-1], sel[403][:120]]  # cut short of the fixed layout
     signers = np.zeros((len(batch), 33), np.uint8)
     want = []
     for i, m in enumerate(batch):
@@ -271,7 +308,7 @@ def test_gossip_device_side_slicing_vs_gossipd(engine, cln):
             want.append(cln.cln_sigcheck_channel_announcement(m, L))
         elif t == b"\x01\x01":
             want.append(cln.cln_sigcheck_node_announcement(m, L))
-        elif t == b"\x01\x02" and len(m) >= 112:
+        elif t == b"\x01\x02" and len(m) >= 138:
             scid = bytes(m[98:106])
             if scid in chans:  # signer by direction bit, as gossmap_manage.c:920-922 selects it
                 nid = chans[scid][m[111] & 1]
