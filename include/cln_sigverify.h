@@ -213,7 +213,8 @@ int sv_get_last_timing(sv_ctx *ctx, float *prep_ms, float *main_ms);
  * SURVEY.md §8d asks to be measured, not assumed). */
 int sv_probe_imad_peak(sv_ctx *ctx, double *imad_per_sec);
 /* individual probes (see engine.cu k_probe_*): 0 IMAD.WIDE peak, 1 4-deep carry chains, 2 fe_mul/s, 3 fe_sqr/s,
- * 4 8-deep carry chains, 5 carry-save, 6 32-bit IMAD lo/hi, 7 IADD3 carry chains, 8 FP64 FMA */
+ * 4 8-deep carry chains, 5 carry-save, 6 32-bit IMAD lo/hi, 7 IADD3 carry chains, 8 FP64 FMA,
+ * 9 / 10: dependent fe_mul / fe_sqr per second of ONE thread on an otherwise idle device (small-batch latency model) */
 int sv_probe(sv_ctx *ctx, int mode, double *ops_per_sec);
 
 /* pinned host memory (cudaHostAlloc) for callers that want full-speed copies */

@@ -594,6 +594,7 @@ __global__ void __launch_bounds__(256) k_probe_addc(int iters, u32* sink) {
 // -------------------------------------------------------------------------------------------------
 // context
 // -------------------------------------------------------------------------------------------------
+#define SV_NSLOTS 2
 struct sv_queue_item {
     int kind;
     u8 msg[32];
@@ -605,18 +606,30 @@ struct sv_ctx {
     int device;
     int sm_count;
     cudaStream_t stream;
+    cudaStream_t stream2;      // second compute stream: consecutive slices of a large host batch alternate streams, so the
+                               // thin last wave of one slice's curve kernel overlaps the next slice's kernels
     cudaStream_t copy_stream;  // H2D of the next slice overlaps the kernels of the current one (sv_verify_host)
     cudaEvent_t h2d_ev[8];
     ge_mem* d_gtab;
     ge_mem* d_bases;
-    qtab_entry* d_scratch;
     size_t scratch_bytes;
     int main_grid;
+    // Launch slots: the scalar-side work records and the per-thread Q-table slab of one prep+main launch pair.  Two slots,
+    // used round-robin, let launches issued on DIFFERENT streams overlap (the partially filled last wave of one batch's
+    // curve kernel runs beside the next batch's kernels); a slot is re-used only after the event recorded behind its
+    // previous use, so calls on one context can never corrupt each other whatever streams the caller picks.
+    struct slot_t {
+        sv_work* d_work;
+        size_t work_cap;
+        qtab_entry* d_scratch;
+        cudaEvent_t done;
+        cudaStream_t last_stream;
+        int used;
+    } slot[SV_NSLOTS];
+    unsigned next_slot;
     // growable device staging for the host-buffer entry points
     size_t cap;  // items
     u8 *d_msg, *d_key, *d_sig, *d_verdict;
-    sv_work* d_work;
-    size_t work_cap;
     // raw-span staging
     u8* d_data;
     size_t data_cap;
@@ -644,6 +657,18 @@ struct dev_tmp {
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
+// every entry point runs on the context's device and puts the caller's current device back on return
+struct dev_guard {
+    int prev = -1;
+    cudaError_t enter(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { prev = -1; return e; }
+        if (prev == dev) { prev = -1; return cudaSuccess; }
+        return cudaSetDevice(dev);
+    }
+    ~dev_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int fail(sv_ctx* ctx, int code, const char* what, cudaError_t e) {
     char buf[512];
     snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
@@ -661,17 +686,36 @@ extern "C" size_t sv_key_size(int kind) {
 }
 extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
-static int ensure_work(sv_ctx* ctx, size_t n) {
-    if (n <= ctx->work_cap) return SV_OK;
-    if (ctx->d_work) cudaFree(ctx->d_work);
-    ctx->d_work = nullptr;
-    ctx->work_cap = 0;
-    CK(cudaMalloc(&ctx->d_work, n * sizeof(sv_work)));
-    ctx->work_cap = n;
+// Pick the next launch slot for n work records on stream st: waits (on the device, not the host) for the slot's previous
+// user if that ran on another stream, grows the record array geometrically when needed (the only host-synchronising case).
+static int acquire_slot(sv_ctx* ctx, size_t n, cudaStream_t st, sv_ctx::slot_t** out) {
+    sv_ctx::slot_t* sl = &ctx->slot[ctx->next_slot++ % SV_NSLOTS];
+    if (sl->used && sl->last_stream != st) CK(cudaStreamWaitEvent(st, sl->done, 0));
+    if (n > sl->work_cap) {
+        if (sl->used) CK(cudaEventSynchronize(sl->done));
+        size_t cap = sl->work_cap ? sl->work_cap : 4096;
+        while (cap < n) cap *= 2;
+        if (sl->d_work) cudaFree(sl->d_work);
+        sl->d_work = nullptr;
+        sl->work_cap = 0;
+        CK(cudaMalloc(&sl->d_work, cap * sizeof(sv_work)));
+        sl->work_cap = cap;
+    }
+    *out = sl;
+    return SV_OK;
+}
+static int release_slot(sv_ctx* ctx, sv_ctx::slot_t* sl, cudaStream_t st) {
+    CK(cudaEventRecord(sl->done, st));
+    sl->last_stream = st;
+    sl->used = 1;
     return SV_OK;
 }
 static int ensure_staging(sv_ctx* ctx, size_t n) {
     if (n <= ctx->cap) return SV_OK;
+    CK(cudaDeviceSynchronize());  // growth only: in-flight launches may still read the old buffers
+    size_t want = ctx->cap ? ctx->cap : 4096;
+    while (want < n) want *= 2;
+    n = want;
     cudaFree(ctx->d_msg); cudaFree(ctx->d_key); cudaFree(ctx->d_sig); cudaFree(ctx->d_verdict);
     ctx->d_msg = ctx->d_key = ctx->d_sig = ctx->d_verdict = nullptr;
     ctx->cap = 0;
@@ -691,18 +735,22 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail(nullptr, SV_ERR_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)", e);
     if (device < 0 || device >= ndev) return fail(nullptr, SV_ERR_ARG, "bad device ordinal", cudaSuccess);
-    CK(cudaSetDevice(device));
+    dev_guard dg__;
+    CK(dg__.enter(device));
     ctx = new sv_ctx();
     ctx->device = device;
-    ctx->cap = ctx->work_cap = ctx->data_cap = ctx->span_cap = 0;
+    ctx->cap = ctx->data_cap = ctx->span_cap = 0;
+    for (int i = 0; i < SV_NSLOTS; i++) { ctx->slot[i].d_work = nullptr; ctx->slot[i].work_cap = 0; ctx->slot[i].d_scratch = nullptr;
+                                          ctx->slot[i].done = nullptr; ctx->slot[i].last_stream = nullptr; ctx->slot[i].used = 0; }
+    ctx->next_slot = 0;
     ctx->d_msg = ctx->d_key = ctx->d_sig = ctx->d_verdict = ctx->d_data = nullptr;
-    ctx->d_work = nullptr; ctx->d_off = nullptr; ctx->d_len = nullptr;
+    ctx->d_off = nullptr; ctx->d_len = nullptr;
     ctx->launches = 0;
     ctx->g_buf = nullptr;
     ctx->g_cap = 0;
     ctx->profiling = 0;
     ctx->ev[0] = ctx->ev[1] = ctx->ev[2] = nullptr;
-    ctx->stream = ctx->copy_stream = nullptr;
+    ctx->stream = ctx->stream2 = ctx->copy_stream = nullptr;
     for (int i = 0; i < 8; i++) ctx->h2d_ev[i] = nullptr;
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
@@ -712,8 +760,10 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     do {
 #define CK2(call) { cudaError_t e2 = (call); if (e2 != cudaSuccess) { rc = fail(nullptr, e2 == cudaErrorMemoryAllocation ? SV_ERR_NOMEM : SV_ERR_CUDA, #call, e2); break; } }
         CK2(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK2(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
         CK2(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; i++) CK2(cudaEventCreateWithFlags(&ctx->h2d_ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 8 && rc == SV_OK; i++) CK2(cudaEventCreateWithFlags(&ctx->h2d_ev[i], cudaEventDisableTiming));
+        if (rc != SV_OK) break;
         CK2(cudaMalloc(&ctx->d_gtab, (size_t)SV_GT_ENTRIES * sizeof(ge_mem)));
         CK2(cudaMalloc(&ctx->d_bases, 16 * sizeof(ge_mem)));
         CK2(cudaMalloc(&ctx->d_sink, 64));
@@ -722,7 +772,11 @@ extern "C" int sv_create(sv_ctx** out, int device) {
         if (occ < 1) occ = 1;
         ctx->main_grid = ctx->sm_count * occ;
         ctx->scratch_bytes = (size_t)ctx->main_grid * SV_MAIN_BLOCK * 8 * sizeof(qtab_entry);
-        CK2(cudaMalloc(&ctx->d_scratch, ctx->scratch_bytes));
+        for (int i = 0; i < SV_NSLOTS && rc == SV_OK; i++) {
+            CK2(cudaMalloc(&ctx->slot[i].d_scratch, ctx->scratch_bytes));
+            CK2(cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming));
+        }
+        if (rc != SV_OK) break;
         k_gtable_bases<<<1, 32, 0, ctx->stream>>>(ctx->d_bases);
         k_gtable_fill<<<(SV_GT_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_gtab, ctx->d_bases);
         ctx->launches += 2;
@@ -737,13 +791,21 @@ extern "C" int sv_create(sv_ctx** out, int device) {
 
 extern "C" void sv_destroy(sv_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_gtab); cudaFree(ctx->d_bases); cudaFree(ctx->d_scratch); cudaFree(ctx->d_sink);
+    dev_guard dg__;
+    dg__.enter(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_gtab); cudaFree(ctx->d_bases); cudaFree(ctx->d_sink);
+    for (int i = 0; i < SV_NSLOTS; i++) {
+        cudaFree(ctx->slot[i].d_scratch);
+        cudaFree(ctx->slot[i].d_work);
+        if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
+    }
     cudaFree(ctx->d_msg); cudaFree(ctx->d_key); cudaFree(ctx->d_sig); cudaFree(ctx->d_verdict);
-    cudaFree(ctx->d_work); cudaFree(ctx->d_data); cudaFree(ctx->d_off); cudaFree(ctx->d_len); cudaFree(ctx->g_buf);
+    cudaFree(ctx->d_data); cudaFree(ctx->d_off); cudaFree(ctx->d_len); cudaFree(ctx->g_buf);
     for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; i++) if (ctx->h2d_ev[i]) cudaEventDestroy(ctx->h2d_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -763,33 +825,38 @@ extern "C" int sv_get_info(const sv_ctx* ctx, sv_info* info) {
     return SV_OK;
 }
 
-// launch prep + main on device-resident SoA arrays
+// launch prep + main on device-resident SoA arrays.  *used (optional) receives the slot whose work records the launch
+// wrote (the gossip status kernel reads their flags afterwards, on the same stream).
 static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
-                         u8* d_verdict, u32* d_bitmap, cudaStream_t st, u8* d_keyok = nullptr) {
+                         u8* d_verdict, u32* d_bitmap, cudaStream_t st, u8* d_keyok = nullptr,
+                         sv_ctx::slot_t** used = nullptr) {
     if (n == 0) return SV_OK;
-    int rc = ensure_work(ctx, n);
+    sv_ctx::slot_t* sl = nullptr;
+    int rc = acquire_slot(ctx, n, st, &sl);
     if (rc) return rc;
+    if (used) *used = sl;
+    sv_work* work = sl->d_work;
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
     if (kind == SV_KIND_SCHNORR) {
-        k_prep_schnorr<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_work);
+        k_prep_schnorr<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_key, d_sig, n, work);
     } else {
         size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
-        k_prep_inv<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_msg, d_sig, n, ctx->d_work);
-        k_prep_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_sig, n, ctx->d_work);
+        k_prep_inv<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_msg, d_sig, n, work);
+        k_prep_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_sig, n, work);
         ctx->launches += 1;
     }
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
     if (kind == SV_KIND_ECDSA33)
-        k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict, d_keyok);
+        k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
     else if (kind == SV_KIND_ECDSA_XY)
-        k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict, d_keyok);
+        k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
     else
     {
-        k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, d_key, d_sig, n, ctx->d_gtab, ctx->d_scratch, d_verdict, d_keyok);
+        k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
         size_t threads = (n + SV_FINAL_BATCH - 1) / SV_FINAL_BATCH;
-        k_final_schnorr<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_work, d_sig, n, d_verdict);
+        k_final_schnorr<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(work, d_sig, n, d_verdict);
         ctx->launches += 1;
     }
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
@@ -800,13 +867,14 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
         ctx->launches += 1;
     }
     CK(cudaGetLastError());
-    return SV_OK;
+    return release_slot(ctx, sl, st);
 }
 
 extern "C" int sv_verify_device(sv_ctx* ctx, int kind, const void* d_msg32, const void* d_key, const void* d_sig64,
                                 size_t n, void* d_verdicts, void* d_bitmap, void* stream) {
     if (!ctx || sv_key_size(kind) == 0 || (n && (!d_msg32 || !d_key || !d_sig64 || !d_verdicts))) return SV_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     return launch_verify(ctx, kind, (const u8*)d_msg32, (const u8*)d_key, (const u8*)d_sig64, n, (u8*)d_verdicts,
                          (u32*)d_bitmap, st);
@@ -814,7 +882,8 @@ extern "C" int sv_verify_device(sv_ctx* ctx, int kind, const void* d_msg32, cons
 
 extern "C" int sv_set_profiling(sv_ctx* ctx, int on) {
     if (!ctx) return SV_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     if (on && !ctx->ev[0])
         for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ctx->ev[i]));
     ctx->profiling = on ? 1 : 0;
@@ -842,45 +911,48 @@ extern "C" int sv_sync(sv_ctx* ctx, void* stream) {
 
 extern "C" int sv_verify_host(sv_ctx* ctx, int kind, const uint8_t* msg32, const uint8_t* key, const uint8_t* sig64,
                               size_t n, uint8_t* verdicts) {
-    size_t ks = sv_key_size(kind);
-    if (!ctx || ks == 0 || (n && (!msg32 || !key || !sig64 || !verdicts))) return SV_ERR_ARG;
+    size_t ks_ = sv_key_size(kind);
+    if (!ctx || ks_ == 0 || (n && (!msg32 || !key || !sig64 || !verdicts))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     size_t chunk = n < SV_HOST_CHUNK ? n : SV_HOST_CHUNK;
     int rc = ensure_staging(ctx, chunk);
     if (rc) return rc;
-    rc = ensure_work(ctx, chunk);
-    if (rc) return rc;
     // Software pipeline inside a chunk: slices sized in whole waves of the persistent grid; slice k+1 is copied on
-    // the copy stream while slice k runs on the compute stream.  First slice small so the kernels start early.
+    // the copy stream while slice k runs; consecutive slices alternate between the two compute streams (each has its own
+    // launch slot), so the partially filled last wave of one slice overlaps the next slice.  First slice small so the
+    // kernels start early.
     const size_t wave = (size_t)ctx->main_grid * SV_MAIN_BLOCK;
     for (size_t off = 0; off < n; off += chunk) {
         size_t c = (n - off < chunk) ? (n - off) : chunk;
         size_t done = 0;
         int k = 0;
+        const bool piped = c > 2 * wave;
         while (done < c) {
-            size_t want = (k == 0) ? 2 * wave : 8 * wave;
+            size_t want = (k == 0) ? 2 * wave : 6 * wave;
             size_t s = (c - done < want + wave) ? (c - done) : want;  // do not leave a sliver behind
             if (k >= 7) s = c - done;
-            cudaStream_t cs = (c > 2 * wave) ? ctx->copy_stream : ctx->stream;
+            cudaStream_t cs = piped ? ctx->copy_stream : ctx->stream;
+            cudaStream_t ks = (piped && (k & 1)) ? ctx->stream2 : ctx->stream;
             CK(cudaMemcpyAsync(ctx->d_msg + 32 * done, msg32 + 32 * (off + done), 32 * s, cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync(ctx->d_key + ks * done, key + ks * (off + done), ks * s, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(ctx->d_key + ks_ * done, key + ks_ * (off + done), ks_ * s, cudaMemcpyHostToDevice, cs));
             CK(cudaMemcpyAsync(ctx->d_sig + 64 * done, sig64 + 64 * (off + done), 64 * s, cudaMemcpyHostToDevice, cs));
-            if (cs != ctx->stream) {
+            if (cs != ks) {
                 CK(cudaEventRecord(ctx->h2d_ev[k], cs));
-                CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_ev[k], 0));
+                CK(cudaStreamWaitEvent(ks, ctx->h2d_ev[k], 0));
             }
-            rc = launch_verify(ctx, kind, ctx->d_msg + 32 * done, ctx->d_key + ks * done, ctx->d_sig + 64 * done, s,
-                               ctx->d_verdict + done, nullptr, ctx->stream);
+            rc = launch_verify(ctx, kind, ctx->d_msg + 32 * done, ctx->d_key + ks_ * done, ctx->d_sig + 64 * done, s,
+                               ctx->d_verdict + done, nullptr, ks);
             if (rc) return rc;
-            CK(cudaMemcpyAsync(verdicts + off + done, ctx->d_verdict + done, s, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(verdicts + off + done, ctx->d_verdict + done, s, cudaMemcpyDeviceToHost, ks));
             done += s;
             k++;
         }
         // the next chunk reuses the staging buffers: its copies must not overtake this chunk's kernels
-        if (off + c < n) CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (piped) CK(cudaStreamSynchronize(ctx->stream2));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
     return SV_OK;
 }
 
@@ -911,7 +983,8 @@ extern "C" int sv_verify_host_raw(sv_ctx* ctx, int kind, const uint8_t* data, si
     size_t ks = sv_key_size(kind);
     if (!ctx || ks == 0 || (n && (!data || !off || !len || !key || !sig64 || !verdicts))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     int rc = ensure_staging(ctx, n);
     if (rc) return rc;
     rc = stage_spans(ctx, data, data_len, off, len, n);
@@ -931,7 +1004,8 @@ extern "C" int sv_sha256d_host(sv_ctx* ctx, const uint8_t* data, size_t data_len
                                const uint32_t* len, size_t n, uint8_t* out32) {
     if (!ctx || (n && (!data || !off || !len || !out32))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     int rc = ensure_staging(ctx, n);
     if (rc) return rc;
     rc = stage_spans(ctx, data, data_len, off, len, n);
@@ -947,7 +1021,8 @@ extern "C" int sv_sha256d_host(sv_ctx* ctx, const uint8_t* data, size_t data_len
 extern "C" int sv_pubkey_parse_host(sv_ctx* ctx, const uint8_t* key33, size_t n, uint8_t* xy64, uint8_t* ok) {
     if (!ctx || (n && (!key33 || !xy64 || !ok))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     int rc = ensure_staging(ctx, n);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_key, key33, 33 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -965,7 +1040,8 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
                                      const uint32_t* msg_len, size_t n_msgs, const uint8_t* cu_signers33, int* status) {
     if (!ctx || (n_msgs && (!blob || !msg_off || !msg_len || !status))) return SV_ERR_ARG;
     if (n_msgs == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     // the host only reads the 2-byte type of each message to lay out the item slots
     std::vector<u32> base(n_msgs);
     size_t items = 0;
@@ -993,9 +1069,12 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
     // one grow-only slab: [msg_off u64][msg_len u32][item_base u32][status int][signers 33B][keyok 1B per item]
     size_t need_g = n_msgs * (8 + 4 + 4 + 4 + 33) + cap + 64;
     if (need_g > ctx->g_cap) {
+        CK(cudaDeviceSynchronize());
+        size_t gcap = ctx->g_cap ? ctx->g_cap : (1u << 16);
+        while (gcap < need_g) gcap *= 2;
         cudaFree(ctx->g_buf); ctx->g_buf = nullptr; ctx->g_cap = 0;
-        CK(cudaMalloc(&ctx->g_buf, need_g));
-        ctx->g_cap = need_g;
+        CK(cudaMalloc(&ctx->g_buf, gcap));
+        ctx->g_cap = gcap;
     }
     u64* d_moff = reinterpret_cast<u64*>(ctx->g_buf);
     u32* d_mlen = reinterpret_cast<u32*>(d_moff + n_msgs);
@@ -1017,9 +1096,11 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
     if (items) {
         k_sha256d<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(ctx->d_data, ctx->d_off, ctx->d_len, items, ctx->d_msg);
         ctx->launches += 1;
-        rc = launch_verify(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, nullptr, st, d_keyok);
+        sv_ctx::slot_t* sl = nullptr;
+        rc = launch_verify(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, nullptr, st, d_keyok, &sl);
         if (rc == SV_OK) {
-            k_gossip_status<<<gm, 128, 0, st>>>(ctx->d_data, d_moff, d_mlen, d_base, n_msgs, ctx->d_verdict, ctx->d_work,
+            // same stream as the launch that wrote the records; the slot is not handed out again before this call returns
+            k_gossip_status<<<gm, 128, 0, st>>>(ctx->d_data, d_moff, d_mlen, d_base, n_msgs, ctx->d_verdict, sl->d_work,
                                                 d_keyok, d_status);
             ctx->launches += 1;
         }
@@ -1037,28 +1118,32 @@ extern "C" int sv_verify_samekey_host(sv_ctx* ctx, int kind, const uint8_t* key,
     size_t ks = sv_key_size(kind);
     if (!ctx || ks == 0 || kind == SV_KIND_SCHNORR || (n && (!key || !msg32 || !sig64 || !verdicts))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     int rc = ensure_staging(ctx, n);
     if (rc) return rc;
-    rc = ensure_work(ctx, n);
-    if (rc) return rc;
-    dev_tmp t_sk;
-    CK(t_sk.alloc(sizeof(sv_shared_key)));
-    sv_shared_key* d_sk = t_sk.as<sv_shared_key>();
     cudaStream_t st = ctx->stream;
+    sv_ctx::slot_t* sl = nullptr;
+    rc = acquire_slot(ctx, n, st, &sl);
+    if (rc) return rc;
+    // the shared key's table lives at the head of the slot's (otherwise unused) per-thread table slab
+    sv_shared_key* d_sk = reinterpret_cast<sv_shared_key*>(sl->d_scratch);
     CK(cudaMemcpyAsync(ctx->d_key, key, ks, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_msg, msg32, 32 * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_sig, sig64, 64 * n, cudaMemcpyHostToDevice, st));
     k_sharedkey_build<<<1, 32, 0, st>>>(kind, ctx->d_key, d_sk);
     size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
-    k_prep_inv<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_msg, ctx->d_sig, n, ctx->d_work);
-    k_prep_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_msg, ctx->d_sig, n, ctx->d_work);
+    k_prep_inv<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(ctx->d_msg, ctx->d_sig, n, sl->d_work);
+    k_prep_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_msg, ctx->d_sig, n, sl->d_work);
     ctx->launches += 1;
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
-    k_main_shared<<<grid, SV_MAIN_BLOCK, 0, st>>>(ctx->d_work, ctx->d_sig, n, ctx->d_gtab, d_sk, ctx->d_verdict);
+    k_main_shared<<<grid, SV_MAIN_BLOCK, 0, st>>>(sl->d_work, ctx->d_sig, n, ctx->d_gtab, d_sk, ctx->d_verdict);
     ctx->launches += 3;
     cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaEventRecord(sl->done, st);
+    sl->last_stream = st;
+    sl->used = 1;
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(verdicts, ctx->d_verdict, n, cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "sv_verify_samekey_host", ce);
@@ -1077,7 +1162,8 @@ extern "C" int sv_verify_tx_host(sv_ctx* ctx, int kind, const sv_tx* txs, const 
         if ((size_t)txs[i].script_off + txs[i].script_len > scripts_len ||
             (size_t)txs[i].out_script_off + txs[i].out_script_len > scripts_len)
             return fail(ctx, SV_ERR_ARG, "script span out of range", cudaSuccess);
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     int rc = ensure_staging(ctx, n);
     if (rc) return rc;
     if (scripts_len + 1 > ctx->data_cap) {
@@ -1085,11 +1171,18 @@ extern "C" int sv_verify_tx_host(sv_ctx* ctx, int kind, const sv_tx* txs, const 
         CK(cudaMalloc(&ctx->d_data, scripts_len + 1));
         ctx->data_cap = scripts_len + 1;
     }
-    dev_tmp t_txs, t_ok;
-    CK(t_txs.alloc(n * sizeof(sv_tx_item)));
-    CK(t_ok.alloc(n));
-    sv_tx_item* d_txs = t_txs.as<sv_tx_item>();
-    u8* d_ok = t_ok.as<u8>();
+    // transaction records + sighash-ok flags in the grow-only auxiliary slab (no allocation on the steady-state call path)
+    size_t need_g = n * sizeof(sv_tx_item) + n + 64;
+    if (need_g > ctx->g_cap) {
+        CK(cudaDeviceSynchronize());
+        size_t cap = ctx->g_cap ? ctx->g_cap : (1u << 16);
+        while (cap < need_g) cap *= 2;
+        cudaFree(ctx->g_buf); ctx->g_buf = nullptr; ctx->g_cap = 0;
+        CK(cudaMalloc(&ctx->g_buf, cap));
+        ctx->g_cap = cap;
+    }
+    sv_tx_item* d_txs = reinterpret_cast<sv_tx_item*>(ctx->g_buf);
+    u8* d_ok = ctx->g_buf + n * sizeof(sv_tx_item);
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(d_txs, txs, n * sizeof(sv_tx_item), cudaMemcpyHostToDevice, st));
     if (scripts_len) CK(cudaMemcpyAsync(ctx->d_data, scripts, scripts_len, cudaMemcpyHostToDevice, st));
@@ -1157,7 +1250,8 @@ extern "C" int sv_flush(sv_ctx* ctx, uint8_t* verdicts, size_t capacity) {
 extern "C" int sv_selftest_host(sv_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
     if (!ctx || op < 0 || op > SV_ST_PREPARE_U1 || (n && (!a || !b || !out))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     dev_tmp ta, tb, to;
     CK(ta.alloc(n * 32));
     CK(tb.alloc(n * 32));
@@ -1178,7 +1272,8 @@ extern "C" int sv_synth_device(sv_ctx* ctx, int kind, uint64_t seed, size_t n, v
                                void* d_sig64, void* stream) {
     if (!ctx || sv_key_size(kind) == 0 || (n && (!d_msg32 || !d_key || !d_sig64))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
-    CK(cudaSetDevice(ctx->device));
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     unsigned grid = (unsigned)((n + 127) / 128);
     if (kind == SV_KIND_ECDSA33)
@@ -1193,10 +1288,12 @@ extern "C" int sv_synth_device(sv_ctx* ctx, int kind, uint64_t seed, size_t n, v
 }
 
 extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
-    if (!ctx || !ops_per_sec || mode < 0 || mode > 8) return SV_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    const int iters = (mode == 2 || mode == 3) ? 2000 : 4000;
-    const int blocks = ctx->sm_count * 8, threads = 256;
+    if (!ctx || !ops_per_sec || mode < 0 || mode > 10) return SV_ERR_ARG;
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
+    const int iters = (mode == 2 || mode == 3 || mode >= 9) ? 2000 : 4000;
+    // modes 9/10: ONE warp on the whole device — the dependent-chain latency of fe_mul / fe_sqr (small-batch path)
+    const int blocks = mode >= 9 ? 1 : ctx->sm_count * 8, threads = mode >= 9 ? 32 : 256;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -1212,6 +1309,8 @@ extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
             case 5: k_probe_carry_save<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
             case 6: k_probe_imad32<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
             case 8: k_probe_dfma<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 9: k_probe_fe<0><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
+            case 10: k_probe_fe<1><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
             default: k_probe_addc<<<blocks, threads, 0, ctx->stream>>>(iters, ctx->d_sink); break;
         }
         CK(cudaEventRecord(e1, ctx->stream));
@@ -1224,8 +1323,9 @@ extern "C" int sv_probe(sv_ctx* ctx, int mode, double* ops_per_sec) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     // operations per thread per launch
-    static const double per_iter[9] = {32.0, 32.0, 2.0, 2.0, 32.0, 32.0, 32.0, 64.0, 32.0};
-    *ops_per_sec = per_iter[mode] * iters * (double)blocks * threads / (best * 1e-3);
+    static const double per_iter[11] = {32.0, 32.0, 2.0, 2.0, 32.0, 32.0, 32.0, 64.0, 32.0, 2.0, 1.0};  // mode 10: two INDEPENDENT squaring chains -> one chain's rate
+    // modes 9/10 report dependent operations per second of ONE thread (the two chains of the probe depend on each other)
+    *ops_per_sec = per_iter[mode] * iters * (mode >= 9 ? 1.0 : (double)blocks * threads) / (best * 1e-3);
     return SV_OK;
 }
 extern "C" int sv_probe_imad_peak(sv_ctx* ctx, double* imad_per_sec) { return sv_probe(ctx, 0, imad_per_sec); }
