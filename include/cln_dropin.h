@@ -13,9 +13,9 @@
  *   check_tx_sigs_batch        the per-HTLC loop of channeld/channeld.c:2215-2232 (one shared key,
  *                              n sighashes, n signatures) as one launch
  *
- * check_tx_sig itself (bitcoin/signature.c:194-221) needs no replacement: it computes the BIP143
- * sighash with libwally on the host and then calls check_signed_hash — it picks up this
- * implementation unchanged.
+ *   check_tx_sig               bitcoin/signature.h:120   (bitcoin/signature.c:194-221) — same signature; the BIP143
+ *                              sighash (bitcoin_tx_hash_for_sig :120-151 -> libwally tx_io.c:660-765) is computed
+ *                              on the device from the wally_tx fields
  *
  * A false return always means "signature invalid" (peer's fault).  Engine failures (no GPU, CUDA
  * error) abort() with a message on stderr, CLN's convention for internal errors
@@ -46,6 +46,58 @@ struct node_id { u8 k[33]; };                                          /* common
 struct bip340sig { u8 u8[64]; };                                       /* bitcoin/signature.h:145-147 */
 enum sighash_type { SIGHASH_ALL = 1, SIGHASH_NONE = 2, SIGHASH_SINGLE = 3, SIGHASH_ANYONECANPAY = 0x80 };
 struct bitcoin_signature { secp256k1_ecdsa_signature s; enum sighash_type sighash_type; }; /* signature.h:47-50 */
+/* libwally's public transaction structs (external/libwally-core/include/wally_transaction.h:89-155), Elements fields
+ * included as CLN builds libwally (no WALLY_ABI_NO_ELEMENTS); only the fields BIP143 commits to are read. */
+struct wally_tx_witness_stack;
+struct wally_tx_input {
+    unsigned char txhash[32];
+    uint32_t index;
+    uint32_t sequence;
+    unsigned char *script;
+    size_t script_len;
+    struct wally_tx_witness_stack *witness;
+    uint8_t features;
+    unsigned char blinding_nonce[32];
+    unsigned char entropy[32];
+    unsigned char *issuance_amount;
+    size_t issuance_amount_len;
+    unsigned char *inflation_keys;
+    size_t inflation_keys_len;
+    unsigned char *issuance_amount_rangeproof;
+    size_t issuance_amount_rangeproof_len;
+    unsigned char *inflation_keys_rangeproof;
+    size_t inflation_keys_rangeproof_len;
+    struct wally_tx_witness_stack *pegin_witness;
+};
+struct wally_tx_output {
+    uint64_t satoshi;
+    unsigned char *script;
+    size_t script_len;
+    uint8_t features;
+    unsigned char *asset;
+    size_t asset_len;
+    unsigned char *value;
+    size_t value_len;
+    unsigned char *nonce;
+    size_t nonce_len;
+    unsigned char *surjectionproof;
+    size_t surjectionproof_len;
+    unsigned char *rangeproof;
+    size_t rangeproof_len;
+};
+struct wally_tx {
+    uint32_t version;
+    uint32_t locktime;
+    struct wally_tx_input *inputs;
+    size_t num_inputs;
+    size_t inputs_allocation_len;
+    struct wally_tx_output *outputs;
+    size_t num_outputs;
+    size_t outputs_allocation_len;
+};
+struct chainparams;
+struct wally_psbt;
+struct bitcoin_tx { struct wally_tx *wtx; const struct chainparams *chainparams; struct wally_psbt *psbt; }; /* bitcoin/tx.h:32-40 */
 #endif
 
 /* Optional: choose the CUDA device (default: $CLN_SIGVERIFY_DEVICE or 0).  The context is created
@@ -60,6 +112,15 @@ bool check_signed_hash_nodeid(const struct sha256_double *hash, const secp256k1_
 bool check_schnorr_sig(const struct sha256 *hash, const secp256k1_pubkey *pubkey, const struct bip340sig *sig);
 void sha256_double(struct sha256_double *shadouble, const void *p, size_t len);
 bool pubkey_from_der(const u8 *der, size_t len, struct pubkey *key);
+
+/* bitcoin/signature.h:120.  Exactly one of redeemscript / witness_script is used (witness_script when non-NULL), both
+ * are tal arrays in CLN: their length comes from tal_bytelen(), the input amount from psbt_input_get_amount(tx->psbt, in)
+ * (bitcoin/signature.c:130).  Those two are CLN-internal functions: when this object is linked into a CLN daemon they are
+ * picked up directly (weak references); a stand-alone user supplies them with cln_sigverify_set_tx_hooks(). */
+bool check_tx_sig(const struct bitcoin_tx *tx, size_t input_num, const u8 *redeemscript, const u8 *witness_script,
+                  const struct pubkey *key, const struct bitcoin_signature *sig);
+void cln_sigverify_set_tx_hooks(size_t (*script_bytelen)(const void *tal_script),
+                                uint64_t (*input_amount_sat)(const struct bitcoin_tx *tx, size_t input_num));
 
 /* channeld HTLC loop: ok[i] = check_signed_hash(&hashes[i], &sigs[i].s, key) for one shared key. */
 void check_tx_sigs_batch(const struct sha256_double *hashes, const struct bitcoin_signature *sigs,

@@ -106,20 +106,27 @@ int sv_verify_samekey_host(sv_ctx *ctx, int kind, const uint8_t *key, const uint
  *      one-output commitment-HTLC transactions of channeld/channeld.c:2215-2232 (shape: common/htlc_tx.c:10-69),
  *      bitcoin_tx_hash_for_sig (bitcoin/signature.c:120-151) -> wally_tx_get_btc_signature_hash ->
  *      bip143_signature_hash (libwally tx_io.c:660-765) + check_signed_hash.  The host passes only the fields of the
- *      preimage; scripts live in one blob.  sighash32_out (optional, n x 32) returns the computed sighashes. ---- */
-#define SV_TX_OUTPUTS_SERIALIZED 1u
+ *      preimage; scripts live in one blob.  Multi-output / multi-input transactions (the commitment transaction itself,
+ *      check_tx_sig in general) pass their serialised outputs / outpoints through the SV_TX_* flags.  sighash32_out (optional, n x 32) returns the computed sighashes. ---- */
+#define SV_TX_OUTPUTS_SERIALIZED 1u /* the out_script span holds the already-serialised outputs to commit to (amount ||
+                                       CompactSize || script, concatenated: all outputs for SIGHASH_ALL, the one at the
+                                       input's index for SIGHASH_SINGLE); output_amount is ignored */
+#define SV_TX_INPUTS_SERIALIZED 2u  /* multi-input transaction: the prevouts span holds every outpoint (36 bytes each), the
+                                       sequences span every nSequence (4 bytes each) — hashPrevouts / hashSequence are
+                                       taken over them; prev_txid/prev_index/sequence still describe THE input being signed */
+#define SV_TX_OUTPUTS_ZERO 4u       /* hashOutputs is 32 zero bytes (SIGHASH_SINGLE with no output at the input's index,
+                                       libwally tx_io.c:725) */
 typedef struct {
     uint32_t version, locktime, sequence, sighash_type; /* sighash_type: SIGHASH_ALL 1 / NONE 2 / SINGLE 3, | 0x80 ANYONECANPAY */
     uint8_t prev_txid[32];                              /* as serialised in the transaction (internal byte order) */
     uint32_t prev_index;
-    uint32_t script_off, script_len;                    /* witness script (scriptCode) inside `scripts` */
-    uint32_t out_script_off, out_script_len;            /* scriptPubKey of the single output inside `scripts` */
-    uint32_t pad;                                       /* 0; or SV_TX_OUTPUTS_SERIALIZED: the out_script span holds the
-                                                           already-serialised outputs to commit to (amount || CompactSize
-                                                           || script, concatenated; all outputs for SIGHASH_ALL, the one
-                                                           at the input's index for SIGHASH_SINGLE) and output_amount is
-                                                           ignored — multi-output (commitment) transactions */
+    uint32_t script_off, script_len;                    /* witness script (scriptCode) inside `scripts`, any length */
+    uint32_t out_script_off, out_script_len;            /* scriptPubKey of the single output inside `scripts` (or the
+                                                           serialised outputs, see SV_TX_OUTPUTS_SERIALIZED) */
+    uint32_t flags;                                     /* 0 for the one-input one-output HTLC shape, or SV_TX_* above */
     uint64_t input_amount, output_amount;               /* satoshi */
+    uint32_t prevouts_off, prevouts_len;                /* SV_TX_INPUTS_SERIALIZED only */
+    uint32_t sequences_off, sequences_len;
 } sv_tx;
 int sv_verify_tx_host(sv_ctx *ctx, int kind, const sv_tx *txs, const uint8_t *scripts, size_t scripts_len,
                       const uint8_t *key, const uint8_t *sig64, size_t n, uint8_t *verdicts, uint8_t *sighash32_out);

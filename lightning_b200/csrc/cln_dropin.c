@@ -110,6 +110,110 @@ bool pubkey_from_der(const u8 *der, size_t len, struct pubkey *key) {
     return true;
 }
 
+/* ---- check_tx_sig (bitcoin/signature.c:194-221): gate on the sighash type, BIP143 sighash on the device from the
+ * wally_tx fields (every output / outpoint is handed over serialised; the host hashes nothing), then the verification ---- */
+struct amount_sat { uint64_t satoshis; };                                        /* common/amount.h */
+extern size_t tal_bytelen(const void *ptr) __attribute__((weak));               /* ccan/tal/tal.h */
+extern struct amount_sat psbt_input_get_amount(const struct wally_psbt *psbt, size_t in) __attribute__((weak)); /* bitcoin/psbt.h */
+static size_t (*g_bytelen)(const void *);
+static uint64_t (*g_input_sat)(const struct bitcoin_tx *, size_t);
+
+void cln_sigverify_set_tx_hooks(size_t (*script_bytelen)(const void *), uint64_t (*input_amount_sat)(const struct bitcoin_tx *, size_t)) {
+    g_bytelen = script_bytelen;
+    g_input_sat = input_amount_sat;
+}
+
+static size_t put_varint(u8 *p, uint64_t v) { /* Bitcoin CompactSize */
+    if (v < 0xfd) { p[0] = (u8)v; return 1; }
+    if (v <= 0xffff) { p[0] = 0xfd; p[1] = (u8)v; p[2] = (u8)(v >> 8); return 3; }
+    p[0] = 0xfe;
+    for (int i = 0; i < 4; i++) p[1 + i] = (u8)(v >> (8 * i));
+    return 5;
+}
+static size_t put_output(u8 *p, const struct wally_tx_output *o) {
+    size_t n = 0;
+    for (int i = 0; i < 8; i++) p[n++] = (u8)(o->satoshi >> (8 * i));
+    n += put_varint(p + n, o->script_len);
+    if (o->script_len) memcpy(p + n, o->script, o->script_len);
+    return n + o->script_len;
+}
+
+bool check_tx_sig(const struct bitcoin_tx *tx, size_t input_num, const u8 *redeemscript, const u8 *witness_script,
+                  const struct pubkey *key, const struct bitcoin_signature *sig) {
+    const u8 *script = witness_script ? witness_script : redeemscript;
+    /* "We only support a limited subset of sighash types." (signature.c:205-211) */
+    if (sig->sighash_type != SIGHASH_ALL) {
+        if (!witness_script) return false;
+        if ((int)sig->sighash_type != (SIGHASH_SINGLE | SIGHASH_ANYONECANPAY)) return false;
+    }
+    const struct wally_tx *w = tx->wtx;
+    if (input_num >= w->num_inputs) { /* assert(input_num < tx->wtx->num_inputs), signature.c:212 */
+        fprintf(stderr, "cln_sigverify: check_tx_sig: input %zu of %zu\n", input_num, w->num_inputs);
+        abort();
+    }
+    size_t script_len;
+    uint64_t amount;
+    if (g_bytelen) script_len = script ? g_bytelen(script) : 0;
+    else if (tal_bytelen) script_len = script ? tal_bytelen(script) : 0;
+    else die("check_tx_sig: no tal_bytelen (cln_sigverify_set_tx_hooks)", -4);
+    if (g_input_sat) amount = g_input_sat(tx, input_num);
+    else if (psbt_input_get_amount) amount = psbt_input_get_amount(tx->psbt, input_num).satoshis;
+    else die("check_tx_sig: no psbt_input_get_amount (cln_sigverify_set_tx_hooks)", -4);
+
+    const bool single = ((int)sig->sighash_type & 0x1f) == SIGHASH_SINGLE;
+    size_t out_bytes = 0;
+    for (size_t i = 0; i < w->num_outputs; i++) out_bytes += 8 + 5 + w->outputs[i].script_len;
+    size_t cap = script_len + out_bytes + 40 * w->num_inputs + 16;
+    u8 *blob = (u8 *)malloc(cap);
+    if (!blob) die("malloc", -3);
+    sv_tx t;
+    memset(&t, 0, sizeof t);
+    size_t n = 0;
+    t.version = w->version;
+    t.locktime = w->locktime;
+    t.sequence = w->inputs[input_num].sequence;
+    t.sighash_type = (uint32_t)sig->sighash_type;
+    memcpy(t.prev_txid, w->inputs[input_num].txhash, 32);
+    t.prev_index = w->inputs[input_num].index;
+    t.input_amount = amount;
+    t.script_off = (uint32_t)n;
+    t.script_len = (uint32_t)script_len;
+    if (script_len) memcpy(blob + n, script, script_len);
+    n += script_len;
+    t.out_script_off = (uint32_t)n;
+    if (single) { /* the output at the input's index, or none (tx_io.c:725-731) */
+        if (input_num < w->num_outputs) { n += put_output(blob + n, &w->outputs[input_num]); t.flags |= SV_TX_OUTPUTS_SERIALIZED; }
+        else t.flags |= SV_TX_OUTPUTS_ZERO;
+    } else {
+        for (size_t i = 0; i < w->num_outputs; i++) n += put_output(blob + n, &w->outputs[i]);
+        t.flags |= SV_TX_OUTPUTS_SERIALIZED;
+    }
+    t.out_script_len = (uint32_t)(n - t.out_script_off);
+    if (w->num_inputs > 1) {
+        t.flags |= SV_TX_INPUTS_SERIALIZED;
+        t.prevouts_off = (uint32_t)n;
+        for (size_t i = 0; i < w->num_inputs; i++) {
+            memcpy(blob + n, w->inputs[i].txhash, 32);
+            for (int b = 0; b < 4; b++) blob[n + 32 + b] = (u8)(w->inputs[i].index >> (8 * b));
+            n += 36;
+        }
+        t.prevouts_len = (uint32_t)(n - t.prevouts_off);
+        t.sequences_off = (uint32_t)n;
+        for (size_t i = 0; i < w->num_inputs; i++) {
+            for (int b = 0; b < 4; b++) blob[n + b] = (u8)(w->inputs[i].sequence >> (8 * b));
+            n += 4;
+        }
+        t.sequences_len = (uint32_t)(n - t.sequences_off);
+    }
+    u8 xy[64], s64[64], v = 0;
+    pubkey_to_xy(xy, &key->pubkey);
+    sig_to_wire(s64, &sig->s);
+    int rc = sv_verify_tx_host(ctx(), SV_KIND_ECDSA_XY, &t, blob, n, xy, s64, 1, &v, NULL);
+    free(blob);
+    if (rc != SV_OK) die("sv_verify_tx_host", rc);
+    return v == 1;
+}
+
 void check_tx_sigs_batch(const struct sha256_double *hashes, const struct bitcoin_signature *sigs,
                          const struct pubkey *key, size_t n, bool *ok) {
     if (n == 0) return;

@@ -1160,7 +1160,10 @@ extern "C" int sv_verify_tx_host(sv_ctx* ctx, int kind, const sv_tx* txs, const 
     if (n == 0) return SV_OK;
     for (size_t i = 0; i < n; i++)
         if ((size_t)txs[i].script_off + txs[i].script_len > scripts_len ||
-            (size_t)txs[i].out_script_off + txs[i].out_script_len > scripts_len)
+            (size_t)txs[i].out_script_off + txs[i].out_script_len > scripts_len ||
+            ((txs[i].flags & SV_TX_INPUTS_SERIALIZED) &&
+             ((size_t)txs[i].prevouts_off + txs[i].prevouts_len > scripts_len ||
+              (size_t)txs[i].sequences_off + txs[i].sequences_len > scripts_len)))
             return fail(ctx, SV_ERR_ARG, "script span out of range", cudaSuccess);
     dev_guard dg__;
     CK(dg__.enter(ctx->device));

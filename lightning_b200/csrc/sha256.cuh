@@ -154,10 +154,16 @@ struct sv_tx_item {
     u32 prev_index;
     u32 script_off, script_len;  // scriptCode = the witness script (bitcoin/script.c:732,849 for HTLCs)
     u32 out_script_off, out_script_len;  // scriptPubKey of the single output
-    u32 pad;
+    u32 flags;                           // SV_TX_* (include/cln_sigverify.h)
     u64 input_amount, output_amount;     // satoshi
+    u32 prevouts_off, prevouts_len;      // SV_TX_INPUTS_SERIALIZED: every outpoint / every nSequence of the transaction
+    u32 sequences_off, sequences_len;
 };
-#define SV_TX_OUTPUTS_SERIALIZED 1u  // sv_tx_item.pad: the out_script span holds already-serialised outputs (see below)
+#ifndef SV_TX_OUTPUTS_SERIALIZED
+#define SV_TX_OUTPUTS_SERIALIZED 1u
+#define SV_TX_INPUTS_SERIALIZED 2u
+#define SV_TX_OUTPUTS_ZERO 4u
+#endif
 
 // incremental SHA-256 (byte granular): lets the preimage stream through without a bound on the script length
 struct sha256_stream {
@@ -217,7 +223,8 @@ SV_HD void sha_stream_final_double(sha256_stream& c, u8 out32[32]) {
 // bound on script sizes.  hashOutputs: by default the transaction has ONE output (output_amount, scriptPubKey span) —
 // the HTLC-transaction shape; with pad == SV_TX_OUTPUTS_SERIALIZED the out_script span holds the serialised outputs to
 // commit to (amount || CompactSize || script, concatenated: all of them for SIGHASH_ALL, the one at the input's index
-// for SIGHASH_SINGLE, tx_io.c:714-737) — what check_tx_sig's adapter passes for commitment transactions.
+// for SIGHASH_SINGLE, tx_io.c:714-737) — what check_tx_sig's adapter passes for commitment transactions.  With
+// SV_TX_INPUTS_SERIALIZED hashPrevouts / hashSequence run over the supplied spans (multi-input transactions).
 SV_HD bool bip143_sighash(u8 out32[32], const sv_tx_item& t, const u8* blob) {
     if (t.sighash_type & 0xffffff00u) {
         for (int i = 0; i < 32; i++) out32[i] = 0;
@@ -229,20 +236,25 @@ SV_HD bool bip143_sighash(u8 out32[32], const sv_tx_item& t, const u8* blob) {
     u8 h_prev[32], h_seq[32], h_out[32];
     sha256_stream c;
     for (int i = 0; i < 32; i++) { h_prev[i] = 0; h_seq[i] = 0; h_out[i] = 0; }
+    const bool multi_in = (t.flags & SV_TX_INPUTS_SERIALIZED) != 0;
     if (!acp) {  // hashPrevouts
         sha_stream_init(c);
-        sha_stream_put(c, t.prev_txid, 32);
-        sha_stream_le(c, t.prev_index, 4);
+        if (multi_in) sha_stream_put(c, blob + t.prevouts_off, t.prevouts_len);
+        else {
+            sha_stream_put(c, t.prev_txid, 32);
+            sha_stream_le(c, t.prev_index, 4);
+        }
         sha_stream_final_double(c, h_prev);
     }
     if (!(acp || sh_single || sh_none)) {  // hashSequence
         sha_stream_init(c);
-        sha_stream_le(c, t.sequence, 4);
+        if (multi_in) sha_stream_put(c, blob + t.sequences_off, t.sequences_len);
+        else sha_stream_le(c, t.sequence, 4);
         sha_stream_final_double(c, h_seq);
     }
-    if (!sh_none) {  // hashOutputs
+    if (!sh_none && !(t.flags & SV_TX_OUTPUTS_ZERO)) {  // hashOutputs
         sha_stream_init(c);
-        if (t.pad == SV_TX_OUTPUTS_SERIALIZED) {
+        if (t.flags & SV_TX_OUTPUTS_SERIALIZED) {
             sha_stream_put(c, blob + t.out_script_off, t.out_script_len);
         } else {
             sha_stream_le(c, t.output_amount, 8);

@@ -30,8 +30,9 @@ class SvTx(ctypes.Structure):
     _fields_ = [("version", ctypes.c_uint32), ("locktime", ctypes.c_uint32), ("sequence", ctypes.c_uint32),
                 ("sighash_type", ctypes.c_uint32), ("prev_txid", ctypes.c_uint8 * 32), ("prev_index", ctypes.c_uint32),
                 ("script_off", ctypes.c_uint32), ("script_len", ctypes.c_uint32), ("out_script_off", ctypes.c_uint32),
-                ("out_script_len", ctypes.c_uint32), ("pad", ctypes.c_uint32), ("input_amount", ctypes.c_uint64),
-                ("output_amount", ctypes.c_uint64)]
+                ("out_script_len", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("input_amount", ctypes.c_uint64),
+                ("output_amount", ctypes.c_uint64), ("prevouts_off", ctypes.c_uint32), ("prevouts_len", ctypes.c_uint32),
+                ("sequences_off", ctypes.c_uint32), ("sequences_len", ctypes.c_uint32)]
 
 
 class SvInfo(ctypes.Structure):

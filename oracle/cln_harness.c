@@ -29,7 +29,14 @@ const struct chainparams *chainparams;
 bool is_elements(const struct chainparams *cp) { (void)cp; return false; }
 void tal_wally_start(void) {}
 void tal_wally_end(const tal_t *parent) { (void)parent; }
-struct amount_sat psbt_input_get_amount(const struct wally_psbt *psbt, size_t in) { (void)psbt; (void)in; abort(); }
+/* the harness's transactions carry no PSBT: the amount of the input being signed is set by the test (cln_tx_set_input_amount) */
+static u64 g_input_amount_sat;
+struct amount_sat psbt_input_get_amount(const struct wally_psbt *psbt, size_t in) {
+    (void)psbt; (void)in;
+    struct amount_sat a;
+    a.satoshis = g_input_amount_sat;
+    return a;
+}
 bool utf8_check(const void *buf, size_t len) { (void)buf; (void)len; return true; }
 char *tal_hexstr(const tal_t *ctx, const void *data, size_t len) {
     static const char d[] = "0123456789abcdef";
@@ -192,4 +199,49 @@ int cln_htlc_sighash(uint32_t version, uint32_t locktime, const u8 *prev_txid32,
                                                   WALLY_TX_FLAG_USE_WITNESS, out32, 32);
     wally_tx_free(tx);
     return rc;
+}
+
+/* ---- check_tx_sig itself (bitcoin/signature.c:194-221), on a struct bitcoin_tx assembled with libwally: any number of
+ * inputs and outputs, so that commitment transactions (BOLT #3 Appendix C, channeld/test/run-commit_tx.c) fit ---- */
+#include <bitcoin/tx.h>
+struct bitcoin_tx *cln_tx_new(uint32_t version, uint32_t locktime) {
+    setup();
+    struct bitcoin_tx *tx = calloc(1, sizeof(*tx));
+    if (wally_tx_init_alloc(version, locktime, 4, 4, &tx->wtx) != WALLY_OK) abort();
+    return tx;
+}
+int cln_tx_add_input(struct bitcoin_tx *tx, const u8 *txid32, uint32_t index, uint32_t sequence) {
+    return wally_tx_add_raw_input(tx->wtx, txid32, 32, index, sequence, NULL, 0, NULL, 0);
+}
+int cln_tx_add_output(struct bitcoin_tx *tx, uint64_t satoshi, const u8 *script, size_t len) {
+    return wally_tx_add_raw_output(tx->wtx, satoshi, script, len, 0);
+}
+void cln_tx_free(struct bitcoin_tx *tx) { wally_tx_free(tx->wtx); free(tx); }
+void cln_tx_set_input_amount(uint64_t sat) { g_input_amount_sat = sat; }
+uint64_t cln_tx_input_amount_hook(const struct bitcoin_tx *tx, size_t in) { (void)tx; (void)in; return g_input_amount_sat; }
+size_t cln_tal_bytelen_hook(const void *p) { return tal_bytelen(p); }
+u8 *cln_tal_bytes(const u8 *p, size_t len) { return tal_dup_arr(NULL, u8, p, len, 0); }
+void cln_tal_free(void *p) { tal_free(p); }
+size_t cln_sizeof_bitcoin_signature(void) { return sizeof(struct bitcoin_signature); }
+/* fills a struct bitcoin_signature and a struct pubkey the way CLN's parsers would; 0 if either fails to parse */
+int cln_make_tx_sig_args(const u8 *sig64, uint32_t sighash_type, const u8 *pub33, void *bitcoin_signature_out, void *pubkey_out) {
+    setup();
+    struct bitcoin_signature *bs = bitcoin_signature_out;
+    struct pubkey *pk = pubkey_out;
+    const u8 *p = sig64;
+    size_t max = 64;
+    fromwire_secp256k1_ecdsa_signature(&p, &max, &bs->s);
+    if (!p) return 0;
+    bs->sighash_type = (enum sighash_type)sighash_type;
+    return pubkey_from_der(pub33, 33, pk) ? 1 : 0;
+}
+void cln_tx_sighash(const struct bitcoin_tx *tx, unsigned in, const u8 *tal_script, uint32_t sighash_type, u8 *out32) {
+    struct sha256_double h;
+    bitcoin_tx_hash_for_sig(tx, in, tal_script, (enum sighash_type)sighash_type, &h);
+    memcpy(out32, h.sha.u.u8, 32);
+}
+/* CLN's own, unmodified check_tx_sig */
+int cln_check_tx_sig(const struct bitcoin_tx *tx, size_t in, const u8 *tal_redeemscript, const u8 *tal_witness_script,
+                     const void *pubkey, const void *bitcoin_signature) {
+    return check_tx_sig(tx, in, tal_redeemscript, tal_witness_script, pubkey, bitcoin_signature) ? 1 : 0;
 }

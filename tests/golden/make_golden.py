@@ -12,6 +12,16 @@ exists; the GPU box only sees the generated files).  Vectors are data, not code:
                           node_announcement, channel_update messages; all signatures valid under the reference)
   chan_ann_3703.json      the mainnet channel_announcement of gossipd/test/run-check_channel_announcement.c
   ecmult_kat.json         the two digests of tests.c:5657-5726 (SHA-256 over x*G for derived scalars)
+  ecdsa_edge_cases.json   the verification cases of test_ecdsa_edge_cases (tests.c:7069-7297): R = infinity, r = 0, s = 0,
+                          message 0 / 1 / -1 with crafted keys, the r + n wrap boundary (r = p - n), the nonce n-1 signature
+                          of key 1, an all-0xff compact signature — as (msg32, pub33, sig64) triples.  The reference
+                          calls its INTERNAL secp256k1_ecdsa_sig_verify there (no low-S rule); each triple records that
+                          internal expectation as the source states it AND the public-API verdict (parse + low-S rule,
+                          what CLN and the engine implement) obtained from oracle/_ref.  (:7300-7406 are nonce-function and
+                          key-export cases of the SIGNING side: not on the verification path.)
+  bolt3_htlc_txs.json     BOLT #3 Appendix C "commitment tx with all five HTLCs untrimmed (minimum feerate)": the five fully
+                          signed HTLC transactions embedded in channeld/test/run-full_channel.c:635-673 (hex), parsed into
+                          the fields BIP143 commits to, with both the remote and the local HTLC signature of each
 
 Every expected verdict written here is re-checked against oracle/_ref (the unmodified reference) at
 generation time.
@@ -236,10 +246,162 @@ def ecmult_kat():
     print("ecmult_kat:", out)
 
 
+def c_bytes(block, name):
+    m = re.search(r"unsigned char " + name + r"\[\d*\]\s*=\s*\{([^}]*)\}", block)
+    assert m, name
+    return bytes(int(x, 16) for x in re.findall(r"0[xX]([0-9A-Fa-f]{2})", m.group(1)))
+
+
+def ecdsa_edge_cases():
+    from tests import adversarial as A
+    N = util.N_ORDER
+    src = open(S + "/src/tests.c").read()
+    body = src[src.index("static void test_ecdsa_edge_cases(void)"):src.index("/* Nonce function corner cases. */")]
+    blk = {}
+    for title, key in (("Verify signature with r of zero fails", "r0"), ("Verify signature with s of zero fails", "s0"),
+                       ("Verify signature with message 0 passes", "m0"), ("Verify signature with message 1 passes", "m1"),
+                       ("Verify signature with message -1 passes", "mm1"), ("Signature where s would be zero", "sz")):
+        i = body.index("/* " + title)
+        blk[key] = body[i:body.index("\n    }\n", i)]
+    b32 = lambda v: (v % 2**256).to_bytes(32, "big")
+    inv = lambda v: pow(v, N - 2, N)
+    G33 = bytes([2 + (A.GY & 1)]) + A.GX.to_bytes(32, "big")
+    cases = []
+
+    def add(name, pub33, r, s, m, internal, note=""):
+        cases.append(dict(name=name, pub33=pub33.hex(), sig64=(b32(r) + b32(s)).hex(), msg32=b32(m).hex(), internal_sig_verify=internal, note=note))
+
+    # tests.c:7073-7087: ss = (-1)^-1, sr = 1, key = 1*G, msg = ss -> the recomputed point is infinity
+    add("infinity (s = -1: high)", G33, 1, inv(N - 1), inv(N - 1), 0)
+    add("infinity, low-S form (r = 1, s = 1, m = -1, key G)", G33, 1, 1, N - 1, 0, "same point at infinity with a low s, so the public API reaches the branch too")
+    add("r = 0", c_bytes(blk["r0"], "pubkey_mods_zero"), 0, 1, 0, 0)
+    add("s = 0", c_bytes(blk["s0"], "pubkey"), 1, 0, 0, 0)
+    for nm in ("pubkey", "pubkey2"):
+        k = c_bytes(blk["m0"], nm)
+        add(f"message 0, {nm}, s = 2", k, 2, 2, 0, 1)
+        add(f"message 0, {nm}, s = -2", k, 2, N - 2, 0, 1, "valid for the internal function, high-S for the API")
+        add(f"message 0, {nm}, s = 1", k, 2, 1, 0, 0)
+    csr = int.from_bytes(c_bytes(blk["m1"], "csr"), "big")
+    for nm in ("pubkey", "pubkey2"):
+        k = c_bytes(blk["m1"], nm)
+        add(f"message 1, {nm}, s = 1", k, csr, 1, 1, 1)
+        add(f"message 1, {nm}, s = -1", k, csr, N - 1, 1, 1, "valid for the internal function, high-S for the API")
+        add(f"message 1, {nm}, s = 1/2", k, csr, inv(2), 1, 0)
+    csr = int.from_bytes(c_bytes(blk["mm1"], "csr"), "big")
+    assert csr == util.P_FIELD - N  # r = p - n: the second x candidate r + n is NOT allowed (ecdsa_impl.h:253)
+    k = c_bytes(blk["mm1"], "pubkey")
+    add("message -1, r = p - n, s = 1", k, csr, 1, N - 1, 1)
+    add("message -1, r = p - n, s = -1", k, csr, N - 1, N - 1, 1, "valid for the internal function, high-S for the API")
+    add("message -1, r = p - n, s = 1/3", k, csr, inv(3), N - 1, 0)
+    # tests.c:7232-7268: key = 1, nonce = n - 1 (nonce2), msg[31] = 0xaa: signing succeeds and the signature verifies
+    msg = bytearray(c_bytes(blk["sz"], "msg"))
+    msg[31] = 0xAA
+    m = int.from_bytes(msg, "big")
+    kk = int.from_bytes(c_bytes(blk["sz"], "nonce2"), "big")
+    R = A.mul(kk, A.G)
+    r = R[0] % N
+    sv = inv(kk) * (m + r * 1) % N
+    if sv > N // 2:
+        sv = N - sv
+    add("key 1, nonce n-1 (tests.c:7251-7258)", G33, r, sv, m, 1)
+    cases.append(dict(name="compact signature of 64 x 0xff does not parse (tests.c:7296)", pub33=G33.hex(), sig64=(b"\xff" * 64).hex(),
+                      msg32=bytes(msg).hex(), internal_sig_verify=None, note="secp256k1_ecdsa_signature_parse_compact == 0"))
+    for c in cases:
+        got = int(util.ref_verify(ref, 0, arr(bytes.fromhex(c["msg32"])).reshape(1, 32), arr(bytes.fromhex(c["pub33"])).reshape(1, 33),
+                                  arr(bytes.fromhex(c["sig64"])).reshape(1, 64))[0])
+        c["expected"] = got
+        s_val = int(c["sig64"][64:], 16)
+        if c["internal_sig_verify"] is not None and s_val <= N // 2:
+            assert got == c["internal_sig_verify"], c  # with a low s the public API and the internal function agree
+        if s_val > N // 2:
+            assert got == 0, c
+    assert sum(c["expected"] for c in cases) >= 6
+    json.dump(cases, open(OUT + "/ecdsa_edge_cases.json", "w"), indent=0)
+    print("ecdsa_edge_cases:", len(cases), "triples,", sum(c["expected"] for c in cases), "valid under the public API")
+
+
+def parse_tx_hex(h):
+    """segwit serialisation -> dict (version, ins[(txid, index, sequence)], outs[(amount, script)], witness[in][items], locktime)"""
+    b = bytes.fromhex(h)
+    pos = 0
+
+    def rd(n):
+        nonlocal pos
+        v = b[pos:pos + n]
+        pos += n
+        return v
+
+    def varint():
+        v = rd(1)[0]
+        if v < 0xfd:
+            return v
+        return int.from_bytes(rd({0xfd: 2, 0xfe: 4, 0xff: 8}[v]), "little")
+    version = int.from_bytes(rd(4), "little")
+    assert rd(2) == b"\x00\x01"
+    ins = []
+    for _ in range(varint()):
+        txid = rd(32)
+        idx = int.from_bytes(rd(4), "little")
+        rd(varint())
+        ins.append((txid, idx, int.from_bytes(rd(4), "little")))
+    outs = []
+    for _ in range(varint()):
+        amt = int.from_bytes(rd(8), "little")
+        outs.append((amt, rd(varint())))
+    wit = [[rd(varint()) for _ in range(varint())] for _ in ins]
+    locktime = int.from_bytes(rd(4), "little")
+    assert pos == len(b)
+    return dict(version=version, ins=ins, outs=outs, witness=wit, locktime=locktime)
+
+
+def bolt3_htlc_txs():
+    cln = util.load_cln()
+    src = open(REF + "/channeld/test/run-full_channel.c").read()
+    hexes = re.findall(r'raw_tx = tx_from_hex\(tmpctx, "([0-9a-f]+)"\);', src)
+    names = re.findall(r"\*\s+(htlc_(?:success|timeout)_tx \(htlc #\d\)): [0-9a-f]+", src)
+    assert len(hexes) == 5 and len(names) == 5
+    # BOLT #3 Appendix C: htlc amounts 1000000 / 2000000 / 2000000 / 3000000 / 4000000 msat; at feerate 0 an HTLC transaction
+    # spends its commitment output without a fee, so the input amount equals the single output's
+    out = []
+    for name, hx in zip(names, hexes):
+        t = parse_tx_hex(hx)
+        assert len(t["ins"]) == 1 and len(t["outs"]) == 1
+        w = t["witness"][0]
+        assert len(w) == 5 and w[0] == b""
+        wscript = w[4]
+        keys = re.findall(rb"\x21([\x02\x03].{32})", wscript, re.S)
+        assert len(keys) == 2  # remote_htlcpubkey, local_htlcpubkey (bitcoin/script.c:732,849)
+        rec = dict(name=name, hex=hx, version=t["version"], locktime=t["locktime"], prev_txid=t["ins"][0][0].hex(),
+                   prev_index=t["ins"][0][1], sequence=t["ins"][0][2], input_amount=t["outs"][0][0], output_amount=t["outs"][0][0],
+                   out_script=t["outs"][0][1].hex(), wscript=wscript.hex(), sigs=[])
+        sh = np.zeros(32, np.uint8)
+        rc = cln.cln_htlc_sighash(ctypes.c_uint32(t["version"]), ctypes.c_uint32(t["locktime"]), t["ins"][0][0], ctypes.c_uint32(t["ins"][0][1]),
+                                  ctypes.c_uint32(t["ins"][0][2]), wscript, ctypes.c_size_t(len(wscript)), ctypes.c_uint64(t["outs"][0][0]),
+                                  ctypes.c_uint64(t["outs"][0][0]), t["outs"][0][1], ctypes.c_size_t(len(t["outs"][0][1])), ctypes.c_uint32(1), P(sh))
+        assert rc == 0
+        rec["sighash"] = bytes(sh).hex()
+        for who, der, key in (("remote_htlc_signature", w[1], keys[0]), ("local_htlc_signature", w[2], keys[1])):
+            assert der[-1] == 1  # SIGHASH_ALL
+            s64 = np.zeros(64, np.uint8)
+            assert ref.ref_sig_der_to_compact(P(arr(der[:-1])), ctypes.c_size_t(len(der) - 1), P(s64))
+            got = int(util.ref_verify(ref, 0, sh.reshape(1, 32), arr(key).reshape(1, 33), s64.reshape(1, 64))[0])
+            assert got == 1, (name, who)  # the spec's vectors verify under the reference with libwally's sighash
+            rec["sigs"].append(dict(who=who, pub33=key.hex(), sig64=bytes(s64).hex(), sighash_type=1, expected=1))
+        out.append(rec)
+    json.dump(out, open(OUT + "/bolt3_htlc_txs.json", "w"), indent=0)
+    print("bolt3_htlc_txs:", len(out), "transactions,", sum(len(o["sigs"]) for o in out), "signatures, all valid under the reference")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # regenerate only the named sets
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     wycheproof()
     bip340()
     pubkey_parse()
     gossip()
     chan_ann_3703()
     ecmult_kat()
+    ecdsa_edge_cases()
+    bolt3_htlc_txs()
