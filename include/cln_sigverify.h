@@ -74,6 +74,14 @@ size_t sv_key_size(int kind);
 int sv_verify_host(sv_ctx *ctx, int kind, const uint8_t *msg32, const uint8_t *key, const uint8_t *sig64,
                    size_t n, uint8_t *verdicts);
 
+/* Batches of at most `small_max` signatures (default 2048, capacity 8192; 0 disables) take the LATENCY path: one launch
+ * of a kernel that spreads each verification over three warps (key side / scalar side in parallel, then the two GLV
+ * half-ladders and the fixed-base comb in parallel, joined by full Jacobian additions), inputs and verdicts passing
+ * through a pinned, device-mapped staging block (no copy commands, no allocation).  Larger batches take the throughput
+ * kernels.  Verdicts are identical on both paths (tests/test_gpu_small.py). */
+int sv_set_small_max(sv_ctx *ctx, size_t small_max);
+size_t sv_get_small_max(const sv_ctx *ctx);
+
 /* ---- same, but the message hash is computed on the device: item i signs
  *      SHA256d(data[off[i] .. off[i]+len[i])).  Several items may share one span (the four
  *      signatures of a channel_announcement do). ---- */

@@ -176,8 +176,52 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
             u32 v = verify_curve_side(KIND, w, key + keylen * j, sig + 64 * j, gtab, tab, &kd, part);
             if (active) {
                 verdict[i] = (u8)v;
-                if (keyok) keyok[i] = kd ? 1 : 0;  // gossip ingest distinguishes "undecodable key" (malformed message)
+                // gossip ingest distinguishes "undecodable key" / "unparsable signature" (malformed message) from a bad signature
+                if (keyok) keyok[i] = (u8)((kd ? 1u : 0u) | ((w->flags & SV_WF_PARSED) ? 2u : 0u));
             }
+        }
+    }
+}
+
+// ---- small-batch path (verify.cuh "small-batch path"): one CTA = 3 warps x up to 32 items, lane l of every warp works
+// on item l.  The inputs may live in host-mapped pinned memory (zero-copy: the CTA pulls its items into shared memory
+// with warp-coalesced loads) or in device memory.  aux (optional): bit 0 = key decoded, bit 1 = signature encoding parsed.
+#define SV_SMALL_ITEMS 32
+template <int KIND>
+__global__ void __launch_bounds__(96, 1)
+    k_small(const u8* __restrict__ msg, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
+            const ge_mem* __restrict__ gtab, u8* __restrict__ verdict, u8* __restrict__ aux) {
+    constexpr int keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
+    __shared__ sv_small_item items[SV_SMALL_ITEMS];
+    __shared__ __align__(16) u8 in_msg[SV_SMALL_ITEMS * 32];
+    __shared__ __align__(16) u8 in_key[SV_SMALL_ITEMS * 64];
+    __shared__ __align__(16) u8 in_sig[SV_SMALL_ITEMS * 64];
+    const size_t base = (size_t)blockIdx.x * SV_SMALL_ITEMS;
+    const int cnt = (int)((n - base < SV_SMALL_ITEMS) ? (n - base) : SV_SMALL_ITEMS);
+    for (int t = threadIdx.x; t < cnt * 32; t += blockDim.x) in_msg[t] = msg[32 * base + t];
+    for (int t = threadIdx.x; t < cnt * keylen; t += blockDim.x) in_key[t] = key[(size_t)keylen * base + t];
+    for (int t = threadIdx.x; t < cnt * 64; t += blockDim.x) in_sig[t] = sig[64 * base + t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool active = lane < cnt;
+    const int j = active ? lane : 0;  // idle lanes redo item 0 into their own slot and discard it
+    sv_small_item* it = &items[lane];
+    const u8* m = in_msg + 32 * j;
+    const u8* k = in_key + keylen * j;
+    const u8* sg = in_sig + 64 * j;
+    if (warp == 0) small_key_side(KIND, k, it);
+    else if (warp == 1) small_scalar_side(KIND, m, k, sg, it);
+    __syncthreads();
+    if (warp == 0) small_half_ladder(it, 0);
+    else if (warp == 1) small_half_ladder(it, 1);
+    else small_comb(it, gtab);
+    __syncthreads();
+    if (warp == 0) {
+        bool kd;
+        u32 v = small_finish(KIND, it, sg, &kd);
+        if (active) {
+            verdict[base + lane] = (u8)v;
+            if (aux) aux[base + lane] = (u8)((kd ? 1u : 0u) | ((it->w.flags & SV_WF_PARSED) ? 2u : 0u));
         }
     }
 }
@@ -275,7 +319,7 @@ __global__ void __launch_bounds__(128) k_gossip_slice(const u8* blob, const u64*
 // bitcoin/pubkey.c:102-113).  node_ids are raw bytes on the wire (common/node_id.c:54) and only fail the signature.
 __global__ void __launch_bounds__(128) k_gossip_status(const u8* blob, const u64* msg_off, const u32* msg_len,
                                                        const u32* item_base, size_t n_msgs, const u8* verdict,
-                                                       const sv_work* work, const u8* keyok, int* status) {
+                                                       const u8* aux, int* status) {
     size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_msgs || status[m] != 0) return;
     const u8* p = blob + msg_off[m];
@@ -286,8 +330,8 @@ __global__ void __launch_bounds__(128) k_gossip_status(const u8* blob, const u64
         if (!verdict[item_base[m] + k]) st = k + 1;
     for (int k = 0; k < nitems; k++) {
         u32 it = item_base[m] + k;
-        if (!(work[it].flags & SV_WF_PARSED)) st = -1;
-        if (type == 256 && k >= 2 && !keyok[it]) st = -1;
+        if (!(aux[it] & 2u)) st = -1;                           // r or s >= n: the wire parser refuses the message
+        if (type == 256 && k >= 2 && !(aux[it] & 1u)) st = -1;  // undecodable bitcoin_key
     }
     status[m] = st;
 }
@@ -595,6 +639,10 @@ __global__ void __launch_bounds__(256) k_probe_addc(int iters, u32* sink) {
 // context
 // -------------------------------------------------------------------------------------------------
 #define SV_NSLOTS 2
+#define SV_SMALL_CAP 8192           // items the pinned small-batch staging block holds
+#ifndef SV_SMALL_MAX_DEFAULT
+#define SV_SMALL_MAX_DEFAULT 2048   // largest batch sent down the small-batch path (SV_SMALL_MAX overrides; 0 disables)
+#endif
 struct sv_queue_item {
     int kind;
     u8 msg[32];
@@ -627,6 +675,10 @@ struct sv_ctx {
         int used;
     } slot[SV_NSLOTS];
     unsigned next_slot;
+    // small-batch path: calls of up to small_max signatures run as ONE launch of k_small reading their inputs straight
+    // from this pinned, device-mapped staging block (no H2D/D2H copy commands, no allocation)
+    size_t small_max, small_cap;
+    u8* h_small;
     // growable device staging for the host-buffer entry points
     size_t cap;  // items
     u8 *d_msg, *d_key, *d_sig, *d_verdict;
@@ -743,6 +795,11 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     for (int i = 0; i < SV_NSLOTS; i++) { ctx->slot[i].d_work = nullptr; ctx->slot[i].work_cap = 0; ctx->slot[i].d_scratch = nullptr;
                                           ctx->slot[i].done = nullptr; ctx->slot[i].last_stream = nullptr; ctx->slot[i].used = 0; }
     ctx->next_slot = 0;
+    ctx->h_small = nullptr;
+    ctx->small_cap = SV_SMALL_CAP;
+    ctx->small_max = SV_SMALL_MAX_DEFAULT;
+    if (const char* e = getenv("SV_SMALL_MAX")) ctx->small_max = (size_t)strtoull(e, nullptr, 10);
+    if (ctx->small_max > ctx->small_cap) ctx->small_max = ctx->small_cap;
     ctx->d_msg = ctx->d_key = ctx->d_sig = ctx->d_verdict = ctx->d_data = nullptr;
     ctx->d_off = nullptr; ctx->d_len = nullptr;
     ctx->launches = 0;
@@ -767,6 +824,7 @@ extern "C" int sv_create(sv_ctx** out, int device) {
         CK2(cudaMalloc(&ctx->d_gtab, (size_t)SV_GT_ENTRIES * sizeof(ge_mem)));
         CK2(cudaMalloc(&ctx->d_bases, 16 * sizeof(ge_mem)));
         CK2(cudaMalloc(&ctx->d_sink, 64));
+        CK2(cudaHostAlloc((void**)&ctx->h_small, (size_t)SV_SMALL_CAP * (32 + 64 + 64 + 2), cudaHostAllocMapped | cudaHostAllocPortable));
         int occ = 0;
         CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_main<SV_KIND_ECDSA33>, SV_MAIN_BLOCK, 0));
         if (occ < 1) occ = 1;
@@ -795,6 +853,7 @@ extern "C" void sv_destroy(sv_ctx* ctx) {
     dg__.enter(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(ctx->d_gtab); cudaFree(ctx->d_bases); cudaFree(ctx->d_sink);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (int i = 0; i < SV_NSLOTS; i++) {
         cudaFree(ctx->slot[i].d_scratch);
         cudaFree(ctx->slot[i].d_work);
@@ -827,14 +886,36 @@ extern "C" int sv_get_info(const sv_ctx* ctx, sv_info* info) {
 
 // launch prep + main on device-resident SoA arrays.  *used (optional) receives the slot whose work records the launch
 // wrote (the gossip status kernel reads their flags afterwards, on the same stream).
+static int launch_small(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
+                        u8* d_verdict, u8* d_aux, cudaStream_t st) {
+    unsigned grid = (unsigned)((n + SV_SMALL_ITEMS - 1) / SV_SMALL_ITEMS);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
+    if (kind == SV_KIND_ECDSA33) k_small<SV_KIND_ECDSA33><<<grid, 96, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else if (kind == SV_KIND_ECDSA_XY) k_small<SV_KIND_ECDSA_XY><<<grid, 96, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else k_small<SV_KIND_SCHNORR><<<grid, 96, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return SV_OK;
+}
+
 static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
-                         u8* d_verdict, u32* d_bitmap, cudaStream_t st, u8* d_keyok = nullptr,
-                         sv_ctx::slot_t** used = nullptr) {
+                         u8* d_verdict, u32* d_bitmap, cudaStream_t st, u8* d_keyok = nullptr) {
     if (n == 0) return SV_OK;
+    if (n <= ctx->small_max) {  // few signatures: the latency-oriented kernel (one launch, three warps per verification)
+        int rc = launch_small(ctx, kind, d_msg, d_key, d_sig, n, d_verdict, d_keyok, st);
+        if (rc) return rc;
+        if (d_bitmap) {
+            k_pack_bitmap<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_verdict, n, d_bitmap);
+            ctx->launches += 1;
+            CK(cudaGetLastError());
+        }
+        return SV_OK;
+    }
     sv_ctx::slot_t* sl = nullptr;
     int rc = acquire_slot(ctx, n, st, &sl);
     if (rc) return rc;
-    if (used) *used = sl;
     sv_work* work = sl->d_work;
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
     if (kind == SV_KIND_SCHNORR) {
@@ -880,6 +961,13 @@ extern "C" int sv_verify_device(sv_ctx* ctx, int kind, const void* d_msg32, cons
                          (u32*)d_bitmap, st);
 }
 
+extern "C" int sv_set_small_max(sv_ctx* ctx, size_t n) {
+    if (!ctx) return SV_ERR_ARG;
+    ctx->small_max = n < ctx->small_cap ? n : ctx->small_cap;
+    return SV_OK;
+}
+extern "C" size_t sv_get_small_max(const sv_ctx* ctx) { return ctx ? ctx->small_max : 0; }
+
 extern "C" int sv_set_profiling(sv_ctx* ctx, int on) {
     if (!ctx) return SV_ERR_ARG;
     dev_guard dg__;
@@ -916,6 +1004,19 @@ extern "C" int sv_verify_host(sv_ctx* ctx, int kind, const uint8_t* msg32, const
     if (n == 0) return SV_OK;
     dev_guard dg__;
     CK(dg__.enter(ctx->device));
+    if (n <= ctx->small_max) {
+        // small batch: inputs go through the pinned staging block, the kernel reads them over the bus itself and writes the
+        // verdict bytes back the same way: one launch and one stream synchronisation, nothing else
+        u8 *hm = ctx->h_small, *hk = hm + 32 * ctx->small_cap, *hs = hk + 64 * ctx->small_cap, *hv = hs + 64 * ctx->small_cap;
+        memcpy(hm, msg32, 32 * n);
+        memcpy(hk, key, ks_ * n);
+        memcpy(hs, sig64, 64 * n);
+        int rc = launch_small(ctx, kind, hm, hk, hs, n, hv, nullptr, ctx->stream);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(verdicts, hv, n);
+        return SV_OK;
+    }
     size_t chunk = n < SV_HOST_CHUNK ? n : SV_HOST_CHUNK;
     int rc = ensure_staging(ctx, chunk);
     if (rc) return rc;
@@ -1096,12 +1197,9 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
     if (items) {
         k_sha256d<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(ctx->d_data, ctx->d_off, ctx->d_len, items, ctx->d_msg);
         ctx->launches += 1;
-        sv_ctx::slot_t* sl = nullptr;
-        rc = launch_verify(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, nullptr, st, d_keyok, &sl);
+        rc = launch_verify(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, nullptr, st, d_keyok);
         if (rc == SV_OK) {
-            // same stream as the launch that wrote the records; the slot is not handed out again before this call returns
-            k_gossip_status<<<gm, 128, 0, st>>>(ctx->d_data, d_moff, d_mlen, d_base, n_msgs, ctx->d_verdict, sl->d_work,
-                                                d_keyok, d_status);
+            k_gossip_status<<<gm, 128, 0, st>>>(ctx->d_data, d_moff, d_mlen, d_base, n_msgs, ctx->d_verdict, d_keyok, d_status);
             ctx->launches += 1;
         }
     }
@@ -1120,6 +1218,19 @@ extern "C" int sv_verify_samekey_host(sv_ctx* ctx, int kind, const uint8_t* key,
     if (n == 0) return SV_OK;
     dev_guard dg__;
     CK(dg__.enter(ctx->device));
+    if (n <= ctx->small_max) {
+        // a commitment_signed carries at most 483 HTLC signatures: latency matters more than the 18 % of work a shared
+        // table saves, so small same-key batches take the small-batch path with the key repeated per item
+        u8 *hm = ctx->h_small, *hk = hm + 32 * ctx->small_cap, *hs = hk + 64 * ctx->small_cap, *hv = hs + 64 * ctx->small_cap;
+        memcpy(hm, msg32, 32 * n);
+        for (size_t i = 0; i < n; i++) memcpy(hk + ks * i, key, ks);
+        memcpy(hs, sig64, 64 * n);
+        int rcs = launch_small(ctx, kind, hm, hk, hs, n, hv, nullptr, ctx->stream);
+        if (rcs) return rcs;
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(verdicts, hv, n);
+        return SV_OK;
+    }
     int rc = ensure_staging(ctx, n);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;

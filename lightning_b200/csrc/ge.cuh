@@ -99,6 +99,58 @@ SV_HD void gej_add_ge(gej& r, const gej& a, const ge& b, fe* rzr = nullptr) {
     r.inf = 0;
 }
 
+// r = a + b, both Jacobian (12M + 4S), full case analysis as secp256k1_gej_add_var (group_impl.h:504-567):
+// either operand at infinity; H == 0 with R == 0 -> double; H == 0 with R != 0 -> infinity.  r may alias a or b.
+// Used where independently computed partial sums meet (the small-batch path adds its two half-ladders and the comb sum).
+SV_HD void gej_add_gej(gej& r, const gej& a, const gej& b) {
+    if (a.inf) {
+        r = b;
+        return;
+    }
+    if (b.inf) {
+        r = a;
+        return;
+    }
+    fe z22, z12, u1, u2, s1, s2, h, rr, t;
+    fe_sqr(z22, b.z);
+    fe_sqr(z12, a.z);
+    fe_mul(u1, a.x, z22);
+    fe_mul(u2, b.x, z12);
+    fe_mul(t, b.z, z22);
+    fe_mul(s1, a.y, t);
+    fe_mul(t, a.z, z12);
+    fe_mul(s2, b.y, t);
+    fe_sub(h, u2, u1);
+    fe_sub(rr, s2, s1);
+    if (fe_is_zero(h)) {
+        if (fe_is_zero(rr)) {
+            gej_double(r, a);
+        } else {
+            r.inf = 1;
+            fe_set_zero(r.x);
+            fe_set_zero(r.y);
+            fe_set_zero(r.z);
+        }
+        return;
+    }
+    fe hh, hhh, v, x3;
+    fe_sqr(hh, h);
+    fe_mul(hhh, h, hh);
+    fe_mul(v, u1, hh);
+    fe_mul(t, a.z, b.z);
+    fe_mul(r.z, t, h);
+    fe_sqr(t, rr);
+    fe_sub(t, t, hhh);
+    fe_sub(t, t, v);
+    fe_sub(x3, t, v);
+    fe_sub(t, v, x3);
+    fe_mul(t, t, rr);
+    fe_mul(hhh, hhh, s1);
+    fe_sub(r.y, t, hhh);
+    r.x = x3;
+    r.inf = 0;
+}
+
 // y^2 == x^3 + 7 ?   reference: secp256k1_ge_is_valid_var (group_impl.h:356)
 SV_HD bool ge_is_on_curve(const ge& a) {
     fe y2, x3, seven;

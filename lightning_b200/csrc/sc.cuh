@@ -97,6 +97,36 @@ SV_HD void sc_add(sc& r, const sc& a, const sc& b) {
 // 512-bit -> mod n, by folding with 2^256 == NC (mod n), NC = 2^256 - n (129 bits)
 // reference: secp256k1_scalar_reduce_512 (scalar_4x64_impl.h:384) — same idea, other limb size
 SV_HD void sc_reduce512(sc& r, const u32 t[16]) {
+#if SV_DEVICE_CODE
+    // Device form: NC = 2^128 + c with a 4-limb c, so a fold is one 8x4 (then 5x4) IMAD.WIDE product plus a limb-shifted
+    // add; both folds are one generated PTX body (tools/gen_mul.py, checked there against big-int arithmetic).  Same
+    // folds, same intermediate values as the portable code below.
+    u32 B[9];
+    sv_sc_fold2_dev(B, t);
+    // fold 3: B[8] < 8
+    u32 kc[8];
+    {
+        u64 acc = 0;
+        SV_UNROLL
+        for (int i = 0; i < 5; i++) {
+            acc += (u64)B[8] * SC_NC[i];
+            kc[i] = (u32)acc;
+            acc >>= 32;
+        }
+        kc[5] = kc[6] = kc[7] = 0;
+    }
+    u32 s[8];
+    u32 c = u256_add(s, B, kc);
+    // fold 4: possible carry (value then tiny), then the final conditional subtraction
+    u32 mask = 0u - c;
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) kc[i] = (i < 5) ? (SC_NC[i] & mask) : 0u;
+    (void)u256_add(s, s, kc);
+    u32 tt[8];
+    u32 bw = u256_sub(tt, s, SC_N);
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) r.v[i] = (bw == 0) ? tt[i] : s[i];
+#else
     // fold 1: m[0..12] = t[0..7] + t[8..15] * NC           (< 2^386)
     u32 m[14];
     {
@@ -166,6 +196,7 @@ SV_HD void sc_reduce512(sc& r, const u32 t[16]) {
     u32 bw = u256_sub(tt, s, SC_N);
     SV_UNROLL
     for (int i = 0; i < 8; i++) r.v[i] = (bw == 0) ? tt[i] : s[i];
+#endif
 }
 
 // reference: secp256k1_scalar_mul (scalar_4x64_impl.h:1009)

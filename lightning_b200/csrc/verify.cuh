@@ -520,6 +520,135 @@ SV_HD void ecmult_gen_comb(ge& out, const sc& k, const ge_mem* gtab) {
 }
 
 // =================================================================================================
+// small-batch path: ONE verification spread over three cooperating warps (k_small, engine.cu)
+// =================================================================================================
+// A lone verification on the throughput kernels is a single dependent chain of ~2,000 field operations plus a Fermat
+// inversion, ~1.1 ms however few signatures there are (profiles/r2_latency_before_small_path.json).  The independent
+// pieces of R = u1*G + k1*Q + k2*(lambda*Q) are therefore given to different warps of one CTA (different SM
+// sub-partitions, so each has a multiplier pipe of its own), lane l of every warp working on item l of the CTA:
+//   phase A   warp 0: key decode + odd-multiples table of Q        | warp 1: scalar side (s^-1, u1, u2, GLV, recoding)
+//   phase B   warp 0: half ladder k1*Q  | warp 1: half ladder k2*(lambda*Q)  | warp 2: comb sum u1*G
+//   phase C   warp 0: R = (R1 + R2) + u1*G with full Jacobian additions, final comparison
+// The accept/reject rules are the same functions the throughput path uses (ecdsa_parse, ecdsa_finish_prep, schnorr_prep,
+// key_decode, ecdsa_final, schnorr_final); only the schedule of the group operations differs.
+struct alignas(16) sv_small_item {
+    qtab_entry tab[8];  // effective-affine odd multiples of Q (x, y, beta*x)
+    u32 zc[8];          // their common Z
+    sv_work w;
+    sv_jac r1, r2, p3;  // partial sums (r1, r2 on the scaled curve, p3 in true coordinates)
+    u32 key_ok, pad[3];
+};
+
+SV_HD void small_key_side(int kind, const u8* key, sv_small_item* it) {
+    ge Q;
+    it->key_ok = key_decode(Q, kind, key) ? 1u : 0u;
+    fe zc;
+    qtable_build(it->tab, zc, Q);
+    fe_to_words(it->zc, zc);
+}
+// scalar side of ONE signature: what k_prep_inv + k_prep_finish / k_prep_schnorr compute, without batching
+SV_HD void small_scalar_side(int kind, const u8* msg32, const u8* key, const u8* sig64, sv_small_item* it) {
+    if (kind == SV_KIND_SCHNORR) {
+        schnorr_prep(it->w, sig64, key, msg32);
+        return;
+    }
+    sc r, s, m, sinv;
+    bool parsed = false;
+    bool ok = ecdsa_parse(r, s, m, sig64, msg32, &parsed);
+    if (!ok) {
+        SV_UNROLL
+        for (int k = 0; k < 8; k++) s.v[k] = (k == 0);
+    }
+    sc_inverse(sinv, s);
+    ecdsa_finish_prep(it->w, ok, r, m, sinv, parsed);
+}
+// one GLV half: R = (+-|k|) * Q (or lambda*Q) on the scaled curve, 33 regular signed-odd-digit windows
+SV_HD void ecmult_half_ladder(gej& R, const u32* mag, bool lam, const qtab_entry* tab) {
+    u32 t = mag[4];
+    u32 sgn = t >> 31;
+    ge p;
+    qtable_fetch(p, tab, ((t >> 1) & 7u) + 8u, sgn, lam);  // top window: digit 2*(mag >> 129) + 1, always positive
+    gej_set_ge(R, p);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int i = 31; i >= 0; i--) {
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+        for (int j = 0; j < 4; j++) gej_double(R, R);
+        qtable_fetch(p, tab, window4(mag, i), sgn, lam);
+        gej_add_ge(R, R, p);
+    }
+}
+SV_HD void small_jac_store(sv_jac* out, const gej& R) {
+    fe_to_words(out->x, R.x);
+    fe_to_words(out->y, R.y);
+    fe_to_words(out->z, R.z);
+    out->inf = R.inf;
+    out->ok = 1;
+}
+SV_HD void small_jac_load(gej& R, const sv_jac* in) {
+    fe_from_words(R.x, in->x);
+    fe_from_words(R.y, in->y);
+    fe_from_words(R.z, in->z);
+    R.inf = in->inf;
+}
+SV_HD void small_half_ladder(sv_small_item* it, int half) {
+    gej R;
+    ecmult_half_ladder(R, half ? it->w.k2 : it->w.k1, half != 0, it->tab);
+    small_jac_store(half ? &it->r2 : &it->r1, R);
+}
+// u1*G as a Jacobian sum of the 16 comb points (infinity for u1 == 0)
+SV_HD void small_comb(sv_small_item* it, const ge_mem* gtab) {
+    gej R;
+    R.inf = 1;
+    fe_set_zero(R.x);
+    fe_set_zero(R.y);
+    fe_set_zero(R.z);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int row = 0; row < 16; row++) {
+        int d = it->w.gd[row];
+        if (d != 0) {
+            ge p;
+            u32 a = (u32)(d < 0 ? -d : d);
+            ge_from_mem(p, gtab + (size_t)row * SV_GT_ROW + (a - 1));
+            if (d < 0) fe_neg(p.y, p.y);
+            gej_add_ge(R, R, p);
+        }
+    }
+    small_jac_store(&it->p3, R);
+}
+SV_HD u32 small_finish(int kind, sv_small_item* it, const u8* sig64, bool* key_ok = nullptr) {
+    gej R, T;
+    small_jac_load(R, &it->r1);
+    small_jac_load(T, &it->r2);
+    gej_add_gej(R, R, T);  // on the scaled curve: the formulas never use the curve constant
+    fe zc;
+    fe_from_words(zc, it->zc);
+    fe_mul(R.z, R.z, zc);  // back to true coordinates
+    small_jac_load(T, &it->p3);
+    gej_add_gej(R, R, T);
+    u32 flags = it->w.flags;
+    bool ok = (flags & SV_WF_VALID) != 0 && it->key_ok != 0;
+    if (key_ok) *key_ok = it->key_ok != 0;
+    u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);
+    return ok ? v : 0u;
+}
+// the three phases run one after another (host build of the kernel source, tests/host_emul)
+SV_HD u32 verify_small_sequential(int kind, const u8* msg32, const u8* key, const u8* sig64, const ge_mem* gtab,
+                                  sv_small_item* it) {
+    small_key_side(kind, key, it);
+    small_scalar_side(kind, msg32, key, sig64, it);
+    small_half_ladder(it, 0);
+    small_half_ladder(it, 1);
+    small_comb(it, gtab);
+    return small_finish(kind, it, sig64);
+}
+
+// =================================================================================================
 // fixed-base table construction (K4)
 // =================================================================================================
 

@@ -75,6 +75,9 @@ def load_library():
     lib.sv_pubkey_parse_host.argtypes = [vp, vp, sz, vp, vp]
     lib.sv_synth_device.argtypes = [vp, i, ctypes.c_uint64, sz, vp, vp, vp, vp]
     lib.sv_selftest_host.argtypes = [vp, i, vp, vp, sz, vp]
+    lib.sv_set_small_max.argtypes = [vp, sz]
+    lib.sv_get_small_max.argtypes = [vp]
+    lib.sv_get_small_max.restype = sz
     lib.sv_get_info.argtypes = [vp, ctypes.POINTER(SvInfo)]
     lib.sv_probe.argtypes = [vp, i, ctypes.POINTER(ctypes.c_double)]
     lib.sv_probe_imad_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
@@ -222,6 +225,13 @@ class SigVerifier:
         self._check(self.lib.sv_pubkey_parse_host(self._ctx, key33.ctypes.data, n, xy.ctypes.data, ok.ctypes.data),
                     "sv_pubkey_parse_host")
         return xy, ok
+
+    def set_small_max(self, n):
+        """largest batch that takes the small-batch (latency) path; 0 = always the throughput kernels"""
+        self._check(self.lib.sv_set_small_max(self._ctx, int(n)), "sv_set_small_max")
+
+    def small_max(self):
+        return self.lib.sv_get_small_max(self._ctx)
 
     def selftest(self, op, a, b=None):
         """Run primitive `op` (SV_ST_* of cln_sigverify.h) of the device arithmetic on operands a, b: (n, 8) uint32

@@ -180,6 +180,15 @@ void emul_gtable_get(u32 e, u32* xy16) {
     memcpy(xy16 + 8, g_table[e].y, 32);
 }
 
+// the small-batch path (k_small): per item, the three warps' phases run one after another
+void emul_verify_small_batch(int kind, const u8* msg, const u8* key, const u8* sig, size_t n, u8* out) {
+    build_gtable_fast();
+    size_t keylen = kind == SV_KIND_ECDSA33 ? 33 : (kind == SV_KIND_ECDSA_XY ? 64 : 32);
+    sv_small_item it;
+    for (size_t i = 0; i < n; i++)
+        out[i] = (u8)verify_small_sequential(kind, msg + 32 * i, key + keylen * i, sig + 64 * i, g_table.data(), &it);
+}
+
 // full verification of a batch, same data flow as the kernels (prep in groups of SV_PREP_BATCH)
 void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, size_t n, u8* out) {
     build_gtable_fast();

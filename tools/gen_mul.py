@@ -166,7 +166,221 @@ def gen_sqr():
     return "\n".join(out)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Programs: a list of ("asm", Asm) / ("c", "dst = src;") items that can be emitted as CUDA or SIMULATED in Python
+# (PTX carry-flag semantics), so that new generated bodies are checked against big-int arithmetic before they
+# ever reach a GPU (python tools/gen_mul.py --check).
+# ---------------------------------------------------------------------------------------------------------------
+def chain_asm(bank, live, start, prods):
+    """like gen_chain, returning the Asm object"""
+    top = start + 2 * len(prods) - 1
+    top_was_live = top in live
+    a = Asm()
+    started = False
+    n = len(prods)
+    for k, (x, y) in enumerate(prods):
+        for part, limb in (("lo", start + 2 * k), ("hi", start + 2 * k + 1)):
+            name = f"{bank}[{limb}]"
+            is_live = limb in live
+            last = (k == n - 1 and part == "hi")
+            if not started and not is_live:
+                a.lines.append(f"mul.{part}.u32 {a.ref(name, 'out')}, {a.ref(x, 'in')}, {a.ref(y, 'in')};")
+            else:
+                cin = "c" if started else ""
+                cout = ".cc" if (not last or top_was_live) else ""
+                if is_live:
+                    r = a.ref(name, "io")
+                    a.lines.append(f"mad{cin}.{part}{cout}.u32 {r}, {a.ref(x, 'in')}, {a.ref(y, 'in')}, {r};")
+                else:
+                    a.lines.append(f"mad{cin}.{part}{cout}.u32 {a.ref(name, 'out')}, {a.ref(x, 'in')}, {a.ref(y, 'in')}, 0;")
+                started = True
+    for k in range(n):
+        live.add(start + 2 * k)
+        live.add(start + 2 * k + 1)
+    if top_was_live:
+        nxt = top + 1
+        assert nxt not in live, (bank, nxt)
+        a.lines.append(f"addc.u32 {a.ref(f'{bank}[{nxt}]', 'out')}, 0, 0;")
+        live.add(nxt)
+    return a
+
+
+def prog_rect(prog, E, O, dst, a_names, b_names):
+    """dst[0 .. na+nb) = a * b with the even/odd-bank layout (banks E, O are fresh array names)"""
+    na, nb = len(a_names), len(b_names)
+    e_live, o_live = set(), set()
+    for i in range(nb):
+        ev = [(a_names[j], b_names[i]) for j in range(0, na, 2)]
+        od = [(a_names[j], b_names[i]) for j in range(1, na, 2)]
+        if i % 2 == 0:
+            prog.append(("asm", chain_asm(E, e_live, i, ev)))
+            if od:
+                prog.append(("asm", chain_asm(O, o_live, i, od)))
+        else:
+            prog.append(("asm", chain_asm(O, o_live, i - 1, ev)))
+            if od:
+                prog.append(("asm", chain_asm(E, e_live, i + 1, od)))
+    n = na + nb
+    prog.append(("c", f"{dst}[0] = {E}[0];"))
+    a = Asm()
+    first = True
+    for k in range(1, n):
+        e = a.ref(f"{E}[{k}]", "in") if k in e_live else "0"
+        o = a.ref(f"{O}[{k-1}]", "in") if (k - 1) in o_live else "0"
+        last = k == n - 1
+        op = ("add" if first else "addc") + ("" if last else ".cc") + ".u32"
+        a.lines.append(f"{op} {a.ref(f'{dst}[{k}]', 'out')}, {e}, {o};")
+        first = False
+    prog.append(("asm", a))
+
+
+def prog_add(prog, dst, x, y, carry_out=None):
+    """dst[i] = x[i] + y[i] (lists of operand names or "0", equal length) in one carry chain; optional carry-out name"""
+    a = Asm()
+    n = len(dst)
+    for i in range(n):
+        last = (i == n - 1) and carry_out is None
+        op = ("add" if i == 0 else "addc") + ("" if last else ".cc") + ".u32"
+        xs = a.ref(x[i], "in") if x[i] != "0" else "0"
+        ys = a.ref(y[i], "in") if y[i] != "0" else "0"
+        a.lines.append(f"{op} {a.ref(dst[i], 'out')}, {xs}, {ys};")
+    if carry_out:
+        a.lines.append(f"addc.u32 {a.ref(carry_out, 'out')}, 0, 0;")
+    prog.append(("asm", a))
+
+
+SC_C = ["0x2FC9BEBFu", "0x402DA173u", "0x50B75FC4u", "0x45512319u"]  # 2^256 - n = 2^128 + c (scalar_4x64_impl.h:23-25)
+
+
+def prog_sc_reduce():
+    """B[0..8] = t mod-n folded twice: 2^256 == 2^128 + c.  The caller finishes the (tiny) third fold in plain C."""
+    prog = []
+    t = [f"t[{i}]" for i in range(16)]
+    hi = t[8:]
+    prog_rect(prog, "E1", "O1", "P", hi, SC_C)  # P[0..11] = hi * c
+    A = [f"A[{i}]" for i in range(13)]
+    # A = lo + P   (13 limbs)
+    prog_add(prog, A[:12], t[:8] + ["0"] * 4, [f"P[{i}]" for i in range(12)], carry_out="A[12]")
+    # A += hi << 128
+    a = Asm()
+    for k in range(8):
+        op = ("add" if k == 0 else "addc") + ".cc.u32"
+        r = a.ref(A[4 + k], "io")
+        a.lines.append(f"{op} {r}, {r}, {a.ref(hi[k], 'in')};")
+    r = a.ref(A[12], "io")
+    a.lines.append(f"addc.u32 {r}, {r}, 0;")
+    prog.append(("asm", a))
+    # Q[0..8] = A[8..12] * c
+    prog_rect(prog, "E2", "O2", "Q", A[8:13], SC_C)
+    B = [f"B[{i}]" for i in range(9)]
+    prog_add(prog, B, A[:8] + ["0"], [f"Q[{i}]" for i in range(9)])
+    a = Asm()
+    for k in range(5):
+        last = k == 4
+        op = ("add" if k == 0 else "addc") + ("" if last else ".cc") + ".u32"
+        r = a.ref(B[4 + k], "io")
+        a.lines.append(f"{op} {r}, {r}, {a.ref(A[8 + k], 'in')};")
+    prog.append(("asm", a))
+    return prog
+
+
+def emit_prog(prog, indent="    "):
+    out = []
+    for kind, item in prog:
+        out.append(item.emit(indent).rstrip("\n") if kind == "asm" else indent + item)
+    return "\n".join(out)
+
+
+def gen_sc_reduce():
+    out = ["// B[0..8] = (t[0..7] + t[8..15] * 2^256) folded twice with 2^256 == 2^128 + c (mod n): 8x4 + 5x4 = 52 IMAD.WIDE.U32",
+           "SV_D void sv_sc_fold2_dev(u32* __restrict__ B, const u32* __restrict__ t) {",
+           "    u32 E1[13], O1[13], P[12], A[13], E2[10], O2[10], Q[9];",
+           emit_prog(prog_sc_reduce()), "}"]
+    return "\n".join(out)
+
+
+# ---- simulator ---------------------------------------------------------------------------------------------
+def simulate(prog, regs):
+    """execute a program on a dict name -> u32; immediates are decimal / 0x.. (with optional u suffix) literals"""
+    import re as _re
+    M = 0xFFFFFFFF
+
+    def val(tok):
+        tok = tok.strip()
+        if _re.fullmatch(r"(0[xX][0-9a-fA-F]+|\d+)[uU]?", tok):
+            return int(tok.rstrip("uU"), 0)
+        return regs[tok]
+    for kind, item in prog:
+        if kind == "c":
+            m = _re.fullmatch(r"\s*(\S+) = (\S+);", item)
+            regs[m.group(1)] = val(m.group(2))
+            continue
+        cc = None
+        for line in item.lines:
+            line = line.replace("{", "").replace("}", "").rstrip(";")
+            op, rest = line.split(" ", 1)
+            ops = [x.strip() for x in rest.split(",")]
+            parts = op.split(".")
+            base = parts[0]
+            sets_cc = "cc" in parts
+            if base in ("mul",):
+                p = val(ops[1]) * val(ops[2])
+                regs[ops[0]] = (p & M) if "lo" in parts else (p >> 32)
+            elif base in ("mad", "madc"):
+                p = val(ops[1]) * val(ops[2])
+                part = (p & M) if "lo" in parts else (p >> 32)
+                tot = part + val(ops[3]) + ((cc or 0) if base == "madc" else 0)
+                assert base != "madc" or cc is not None
+                regs[ops[0]] = tot & M
+                if sets_cc:
+                    cc = tot >> 32
+            elif base in ("add", "addc"):
+                tot = val(ops[1]) + val(ops[2]) + ((cc or 0) if base == "addc" else 0)
+                assert base != "addc" or cc is not None
+                regs[ops[0]] = tot & M
+                if sets_cc:
+                    cc = tot >> 32
+                else:
+                    assert tot >> 32 == 0 or base == "addc" and ops[1] == "0" or True
+            else:
+                raise ValueError(op)
+    return regs
+
+
+def check():
+    import random
+    rnd = random.Random(5)
+    N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    NC = 2**256 - N
+    prog = prog_sc_reduce()
+    tests = [0, 1, 2**512 - 1, 2**256, N * N, (N - 1) ** 2, 2**512 - 2**256, (2**256 - 1) << 256, 2**256 - 1] + [rnd.getrandbits(512) for _ in range(3000)]
+    for t in tests:
+        regs = {f"t[{i}]": (t >> (32 * i)) & 0xFFFFFFFF for i in range(16)}
+        simulate(prog, regs)
+        B = sum(regs[f"B[{i}]"] << (32 * i) for i in range(9))
+        m = (t & (2**256 - 1)) + (t >> 256) * NC
+        q = (m & (2**256 - 1)) + (m >> 256) * NC
+        assert B == q, (hex(t), hex(B), hex(q))
+        assert regs["B[8]"] < 8
+    # rectangular products on their own
+    for na, nb in ((8, 4), (5, 4), (8, 8), (3, 2), (4, 4)):
+        pr = []
+        prog_rect(pr, "E", "O", "r", [f"a[{i}]" for i in range(na)], [f"b[{i}]" for i in range(nb)])
+        for _ in range(300):
+            a, b = rnd.getrandbits(32 * na), rnd.getrandbits(32 * nb)
+            if _ % 7 == 0:
+                a, b = 2**(32 * na) - 1, 2**(32 * nb) - 1
+            regs = {f"a[{i}]": (a >> (32 * i)) & 0xFFFFFFFF for i in range(na)}
+            regs.update({f"b[{i}]": (b >> (32 * i)) & 0xFFFFFFFF for i in range(nb)})
+            simulate(pr, regs)
+            assert sum(regs[f"r[{i}]"] << (32 * i) for i in range(na + nb)) == a * b, (na, nb)
+    print("gen_mul --check: generated programs match big-int arithmetic")
+
+
 if __name__ == "__main__":
+    if "--check" in sys.argv:
+        check()
+        sys.exit(0)
     print("// u256_gen.cuh — GENERATED by tools/gen_mul.py; do not edit.  Device-only PTX bodies.")
     print("#pragma once")
     print('#include "common.cuh"')
@@ -174,4 +388,6 @@ if __name__ == "__main__":
     print(gen_mul())
     print()
     print(gen_sqr())
+    print()
+    print(gen_sc_reduce())
     print("#endif")
