@@ -82,6 +82,15 @@ int sv_verify_host(sv_ctx *ctx, int kind, const uint8_t *msg32, const uint8_t *k
 int sv_set_small_max(sv_ctx *ctx, size_t small_max);
 size_t sv_get_small_max(const sv_ctx *ctx);
 
+/* ---- MIXED batch (BASELINE config C3: interleaved ECDSA + BIP-340): kinds[i] is the SV_KIND_* tag of item i, keys sit
+ *      in 64-byte slots (the first 33 / 64 / 32 bytes are the key).  The batch is split per kind on the device (index
+ *      lists by warp-aggregated atomics, gather, per-kind kernels, scatter); verdicts come back in item order; an
+ *      unknown tag yields verdict 0. ---- */
+int sv_verify_mixed_host(sv_ctx *ctx, const uint8_t *kinds, const uint8_t *msg32, const uint8_t *key64,
+                         const uint8_t *sig64, size_t n, uint8_t *verdicts);
+int sv_verify_mixed_device(sv_ctx *ctx, const void *d_kinds, const void *d_msg32, const void *d_key64,
+                           const void *d_sig64, size_t n, void *d_verdicts, void *stream);
+
 /* ---- same, but the message hash is computed on the device: item i signs
  *      SHA256d(data[off[i] .. off[i]+len[i])).  Several items may share one span (the four
  *      signatures of a channel_announcement do). ---- */

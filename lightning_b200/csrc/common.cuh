@@ -45,7 +45,9 @@
 // (variant) the last, partial round runs with fewer warps per CTA: COUNTED named barrier, count in a register
 #define SV_SYNC(n) asm volatile("bar.sync 1, %0;" ::"r"(n))
 #else
-#define SV_SYNC(n) __syncthreads()
+// n = number of threads taking part (the whole CTA) or 0: no barrier (callers that run in ONE warp of a larger CTA — the
+// small-batch kernel — must not hit CTA-wide barriers)
+#define SV_SYNC(n) do { if (n) __syncthreads(); } while (0)
 #endif
 #else
 #define SV_SYNC(n) ((void)(n))

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
         size_t i = base + threadIdx.x;
         bool active = i < n;
         size_t j = active ? i : 0;
-        const unsigned part = 0;
+        const unsigned part = SV_MAIN_BLOCK;  // every thread of the CTA reaches every re-convergence barrier
 #else
     // VARIANT (measured 1.3 % slower at 1 M, profiles/r1_variants.md): interleaved item mapping — in round k thread t of
     // CTA c takes item k*T + t*G + c, so a partial last round keeps the first warps of EVERY CTA busy, the idle warps
@@ -224,6 +224,46 @@ __global__ void __launch_bounds__(96, 1)
             if (aux) aux[base + lane] = (u8)((kd ? 1u : 0u) | ((it->w.flags & SV_WF_PARSED) ? 2u : 0u));
         }
     }
+}
+
+// ---- mixed batches (config C3: interleaved ECDSA + BIP-340 with a 1-byte kind tag per item) ---------------------
+// The curve kernels are specialised per kind (a warp must be homogeneous), so a mixed batch is split on the DEVICE:
+// k_mixed_index appends every item to its kind's index list (warp-aggregated atomics), k_mixed_gather copies each kind's
+// items into that kind's dense SoA region, the per-kind kernels run, k_mixed_scatter puts the verdicts back in item order.
+__global__ void __launch_bounds__(256) k_mixed_index(const u8* __restrict__ kinds, size_t n, u32* __restrict__ count,
+                                                     u32* __restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 k = (i < n) ? kinds[i] : 3u;
+    if (k > 2u) k = 3u;  // unknown kind: no list (verdict stays 0)
+    unsigned peers = __match_any_sync(0xFFFFFFFFu, k);
+    if (k < 3u) {
+        int leader = __ffs(peers) - 1;
+        u32 base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&count[k], (u32)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        u32 rank = (u32)__popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+        idx[(size_t)k * n + base + rank] = (u32)i;
+    }
+}
+__global__ void __launch_bounds__(256) k_mixed_gather(const u32* __restrict__ idx, size_t c, int keylen,
+                                                      const u8* __restrict__ msg, const u8* __restrict__ key64,
+                                                      const u8* __restrict__ sig, u8* __restrict__ o_msg,
+                                                      u8* __restrict__ o_key, u8* __restrict__ o_sig) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c) return;
+    size_t i = idx[j];
+    const uint4* m = reinterpret_cast<const uint4*>(msg + 32 * i);
+    const uint4* sg = reinterpret_cast<const uint4*>(sig + 64 * i);
+    uint4* om = reinterpret_cast<uint4*>(o_msg + 32 * j);
+    uint4* os = reinterpret_cast<uint4*>(o_sig + 64 * j);
+    om[0] = m[0]; om[1] = m[1];
+    os[0] = sg[0]; os[1] = sg[1]; os[2] = sg[2]; os[3] = sg[3];
+    for (int b = 0; b < keylen; b++) o_key[(size_t)keylen * j + b] = key64[64 * i + b];
+}
+__global__ void __launch_bounds__(256) k_mixed_scatter(const u32* __restrict__ idx, size_t c, const u8* __restrict__ v,
+                                                       u8* __restrict__ out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < c) out[idx[j]] = v[j];
 }
 
 // ---- one key, many signatures (N3): build the key's table once, then a ladder-only curve kernel --------------
@@ -1315,6 +1355,89 @@ extern "C" int sv_verify_tx_host(sv_ctx* ctx, int kind, const sv_tx* txs, const 
     }
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(ctx, SV_ERR_CUDA, "sv_verify_tx_host", ce);
+    return SV_OK;
+}
+
+// ---- mixed batches: kinds[n] tags, keys in 64-byte slots (the first 33 / 64 / 32 bytes used) ----------------------
+static int ensure_gbuf(sv_ctx* ctx, size_t need) {
+    if (need <= ctx->g_cap) return SV_OK;
+    CK(cudaDeviceSynchronize());
+    size_t cap = ctx->g_cap ? ctx->g_cap : (1u << 16);
+    while (cap < need) cap *= 2;
+    cudaFree(ctx->g_buf); ctx->g_buf = nullptr; ctx->g_cap = 0;
+    CK(cudaMalloc(&ctx->g_buf, cap));
+    ctx->g_cap = cap;
+    return SV_OK;
+}
+// inputs already on the device; scratch = [count u32 x4][idx u32 x 3n]; staging = the context's SoA staging arrays
+static int mixed_device(sv_ctx* ctx, const u8* d_kinds, const u8* d_msg, const u8* d_key64, const u8* d_sig, size_t n,
+                        u8* d_out, u32* d_scratch, cudaStream_t st) {
+    u32* d_count = d_scratch;
+    u32* d_idx = d_scratch + 4;
+    CK(cudaMemsetAsync(d_count, 0, 16, st));
+    CK(cudaMemsetAsync(d_out, 0, n, st));
+    k_mixed_index<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_kinds, n, d_count, d_idx);
+    ctx->launches += 1;
+    u32 count[4];
+    CK(cudaMemcpyAsync(count, d_count, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));  // the per-kind launch sizes are needed on the host
+    size_t o = 0;
+    for (int kind = 0; kind < 3; kind++) {
+        size_t c = count[kind];
+        if (!c) continue;
+        size_t ks = sv_key_size(kind);
+        u8 *om = ctx->d_msg + 32 * o, *ok = ctx->d_key + 64 * o, *os = ctx->d_sig + 64 * o, *ov = ctx->d_verdict + o;
+        const u32* list = d_idx + (size_t)kind * n;
+        k_mixed_gather<<<(unsigned)((c + 255) / 256), 256, 0, st>>>(list, c, (int)ks, d_msg, d_key64, d_sig, om, ok, os);
+        int rc = launch_verify(ctx, kind, om, ok, os, c, ov, nullptr, st);
+        if (rc) return rc;
+        k_mixed_scatter<<<(unsigned)((c + 255) / 256), 256, 0, st>>>(list, c, ov, d_out);
+        ctx->launches += 2;
+        o += c;
+    }
+    CK(cudaGetLastError());
+    return SV_OK;
+}
+extern "C" int sv_verify_mixed_device(sv_ctx* ctx, const void* d_kinds, const void* d_msg32, const void* d_key64,
+                                      const void* d_sig64, size_t n, void* d_verdicts, void* stream) {
+    if (!ctx || (n && (!d_kinds || !d_msg32 || !d_key64 || !d_sig64 || !d_verdicts))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    rc = ensure_gbuf(ctx, 16 + 12 * n + 64);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    return mixed_device(ctx, (const u8*)d_kinds, (const u8*)d_msg32, (const u8*)d_key64, (const u8*)d_sig64, n,
+                        (u8*)d_verdicts, reinterpret_cast<u32*>(ctx->g_buf), st);
+}
+extern "C" int sv_verify_mixed_host(sv_ctx* ctx, const uint8_t* kinds, const uint8_t* msg32, const uint8_t* key64,
+                                    const uint8_t* sig64, size_t n, uint8_t* verdicts) {
+    if (!ctx || (n && (!kinds || !msg32 || !key64 || !sig64 || !verdicts))) return SV_ERR_ARG;
+    if (n == 0) return SV_OK;
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    // aux slab: [count + idx lists][kinds n][msg 32n][key 64n][sig 64n][out n], 16-byte aligned pieces
+    size_t a = (16 + 12 * n + 15) & ~(size_t)15, need = a + ((n + 15) & ~(size_t)15) * 2 + 160 * n + 64;
+    rc = ensure_gbuf(ctx, need);
+    if (rc) return rc;
+    u8* d_kinds = ctx->g_buf + a;
+    u8* d_m = d_kinds + ((n + 15) & ~(size_t)15);
+    u8* d_k = d_m + 32 * n;
+    u8* d_s = d_k + 64 * n;
+    u8* d_o = d_s + 64 * n;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_kinds, kinds, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_m, msg32, 32 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_k, key64, 64 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_s, sig64, 64 * n, cudaMemcpyHostToDevice, st));
+    rc = mixed_device(ctx, d_kinds, d_m, d_k, d_s, n, d_o, reinterpret_cast<u32*>(ctx->g_buf), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(verdicts, d_o, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return SV_OK;
 }
 

@@ -71,11 +71,23 @@ SV_HD void fe_add(fe& r, const fe& a, const fe& b) {
     u32 c = u256_add(r.v, a.v, b.v);
 #if SV_DEVICE_CODE
     u32 k;
+#ifdef SV_ALU_FOLDS
+    // c is 0 or 1: c * 977 as a select, so the fold stays off the multiplier pipe (the curve kernel's bottleneck)
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 kc;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "selp.u32 kc, 977, 0, p;\n\t"
+        "add.cc.u32 %0, %0, kc;\n\t"
+        "addc.cc.u32 %1, %1, %3;\n\t"
+        "addc.u32 %2, 0, 0;\n\t}"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "=r"(k)
+        : "r"(c));
+#else
     asm("mad.lo.cc.u32 %0, %3, 977, %0;\n\t"
         "addc.cc.u32 %1, %1, %3;\n\t"
         "addc.u32 %2, 0, 0;"
         : "+r"(r.v[0]), "+r"(r.v[1]), "=r"(k)
         : "r"(c));
+#endif
     if (k) {
         u32 c2;
         asm("add.cc.u32 %0, %0, 1;\n\t"
@@ -111,12 +123,24 @@ SV_HD void fe_sub(fe& r, const fe& a, const fe& b) {
     // a - b + 2^256 == a - b + (2^32+977): take the constant back out; the borrow past limb 1 is as rare as the
     // carry in fe_add and handled the same way.
 #if SV_DEVICE_CODE
-    u32 k, kc = bw * SV_PC;
+    u32 k;
+#ifdef SV_ALU_FOLDS
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 kc;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "selp.u32 kc, 977, 0, p;\n\t"
+        "sub.cc.u32 %0, %0, kc;\n\t"
+        "subc.cc.u32 %1, %1, %3;\n\t"
+        "subc.u32 %2, 0, 0;\n\t}"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "=r"(k)
+        : "r"(bw));
+#else
+    u32 kc = bw * SV_PC;
     asm("sub.cc.u32 %0, %0, %4;\n\t"
         "subc.cc.u32 %1, %1, %3;\n\t"
         "subc.u32 %2, 0, 0;"
         : "+r"(r.v[0]), "+r"(r.v[1]), "=r"(k)
         : "r"(bw), "r"(kc));
+#endif
     if (k) {
         u32 b2;
         asm("sub.cc.u32 %0, %0, 1;\n\t"
@@ -285,6 +309,34 @@ SV_HD void fe_reduce512(fe& r, const u32 t[16]) {
         : "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]), "=r"(s[9])
         : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]),
           "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]));
+#ifdef SV_REDUCE_NOACC
+    // VARIANT: products with a zero accumulator (fresh aligned register pairs, no pair-forming moves on the multiplier
+    // pipe), added with ALU carry chains
+    u32 pe[8];
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(pe[0]), "=r"(pe[1]), "=r"(pe[2]), "=r"(pe[3]), "=r"(pe[4]), "=r"(pe[5]), "=r"(pe[6]), "=r"(pe[7])
+        : "r"(t[8]), "r"(t[10]), "r"(t[12]), "r"(t[14]), "r"(SV_PC));
+    asm("add.cc.u32 %0, %0, %10;\n\t"
+        "addc.cc.u32 %1, %1, %11;\n\t"
+        "addc.cc.u32 %2, %2, %12;\n\t"
+        "addc.cc.u32 %3, %3, %13;\n\t"
+        "addc.cc.u32 %4, %4, %14;\n\t"
+        "addc.cc.u32 %5, %5, %15;\n\t"
+        "addc.cc.u32 %6, %6, %16;\n\t"
+        "addc.cc.u32 %7, %7, %17;\n\t"
+        "addc.cc.u32 %8, %8, 0;\n\t"
+        "addc.u32 %9, %9, 0;"
+        : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]),
+          "+r"(s[8]), "+r"(s[9])
+        : "r"(pe[0]), "r"(pe[1]), "r"(pe[2]), "r"(pe[3]), "r"(pe[4]), "r"(pe[5]), "r"(pe[6]), "r"(pe[7]));
+#else
     // s[0..8] += {hi0,hi2,hi4,hi6} * 977  (even columns)
     asm("mad.lo.cc.u32 %0, %10, %14, %0;\n\t"
         "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
@@ -299,6 +351,7 @@ SV_HD void fe_reduce512(fe& r, const u32 t[16]) {
         : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]),
           "+r"(s[8]), "+r"(s[9])
         : "r"(t[8]), "r"(t[10]), "r"(t[12]), "r"(t[14]), "r"(SV_PC));
+#endif
     // o[0..7] = {hi1,hi3,hi5,hi7} * 977 (odd columns: limb positions 1..8)
     u32 o[8];
     asm("mul.lo.u32 %0, %8, %12;\n\t"

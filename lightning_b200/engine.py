@@ -75,6 +75,8 @@ def load_library():
     lib.sv_pubkey_parse_host.argtypes = [vp, vp, sz, vp, vp]
     lib.sv_synth_device.argtypes = [vp, i, ctypes.c_uint64, sz, vp, vp, vp, vp]
     lib.sv_selftest_host.argtypes = [vp, i, vp, vp, sz, vp]
+    lib.sv_verify_mixed_host.argtypes = [vp, vp, vp, vp, vp, sz, vp]
+    lib.sv_verify_mixed_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]
     lib.sv_set_small_max.argtypes = [vp, sz]
     lib.sv_get_small_max.argtypes = [vp]
     lib.sv_get_small_max.restype = sz
@@ -225,6 +227,16 @@ class SigVerifier:
         self._check(self.lib.sv_pubkey_parse_host(self._ctx, key33.ctypes.data, n, xy.ctypes.data, ok.ctypes.data),
                     "sv_pubkey_parse_host")
         return xy, ok
+
+    def verify_mixed(self, kinds, msg32, key64, sig64):
+        """Interleaved batch: kinds (n,) uint8 SV_KIND_* tags, keys in 64-byte slots; verdicts in item order."""
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8).reshape(-1)
+        msg32, key64, sig64 = _u8(msg32, 32), _u8(key64, 64), _u8(sig64, 64)
+        n = kinds.shape[0]
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self.lib.sv_verify_mixed_host(self._ctx, kinds.ctypes.data, msg32.ctypes.data, key64.ctypes.data,
+                                                  sig64.ctypes.data, n, out.ctypes.data), "sv_verify_mixed_host")
+        return out[:n]
 
     def set_small_max(self, n):
         """largest batch that takes the small-batch (latency) path; 0 = always the throughput kernels"""

@@ -210,6 +210,59 @@ void ref_make_ecdsa_batch(uint64_t seed, size_t n, uint8_t *msg, uint8_t *pub33,
     }
 }
 
+/* BIP-340 counterpart (config C3): x-only keys, secp256k1_schnorrsig_sign32 with aux_rand = NULL (deterministic); every
+ * 10th item corrupted, classes round-robin {msg bit, R.x bit, s bit, r >= p, s >= n, negated R (odd y), neighbour's key,
+ * key x not on the curve}. */
+typedef struct { uint64_t seed; size_t lo, hi; uint8_t *msg, *xonly, *sig; } sgen_t;
+static void *sgen_worker(void *arg) {
+    sgen_t *g = (sgen_t *)arg;
+    for (size_t i = g->lo; i < g->hi; i++) {
+        uint64_t st = g->seed ^ (0xD1B54A32D192ED03ULL * (i + 1));
+        uint8_t sk[32];
+        for (int k = 0; k < 4; k++) { uint64_t v = splitmix(&st); memcpy(sk + 8 * k, &v, 8); }
+        for (int k = 0; k < 4; k++) { uint64_t v = splitmix(&st); memcpy(g->msg + 32 * i + 8 * k, &v, 8); }
+        sk[0] &= 0x7f; sk[31] |= 1;
+        ref_schnorr_sign(sk, g->msg + 32 * i, g->sig + 64 * i, g->xonly + 32 * i);
+    }
+    return NULL;
+}
+void ref_make_schnorr_batch(uint64_t seed, size_t n, uint8_t *msg, uint8_t *xonly32, uint8_t *sig, int nthreads) {
+    (void)ctx();
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    sgen_t *jobs = (sgen_t *)malloc(sizeof(sgen_t) * (size_t)nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (sgen_t){seed, n * (size_t)t / (size_t)nthreads, n * (size_t)(t + 1) / (size_t)nthreads, msg, xonly32, sig};
+        pthread_create(&th[t], NULL, sgen_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+    static const uint8_t fieldp[32] = {0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,
+                                       0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFE,0xFF,0xFF,0xFC,0x2F};
+    for (size_t i = 0, cls = 0; i < n; i += 10, cls++) {
+        size_t j = (i + 1) % n;
+        switch (cls % 8) {
+        case 0: msg[32 * i + 5] ^= 4; break;
+        case 1: sig[64 * i + 7] ^= 1; break;
+        case 2: sig[64 * i + 40] ^= 1; break;
+        case 3: memset(sig + 64 * i, 0xFF, 32); break;      /* r >= p */
+        case 4: memset(sig + 64 * i + 32, 0xFF, 32); break; /* s >= n */
+        case 5: { /* R.x kept, so R = lift_x is unchanged; instead negate s: verifies to -R side -> x differs */
+            int borrow = 0;
+            static const uint8_t order[32] = {0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFF,0xFE,
+                                              0xBA,0xAE,0xDC,0xE6,0xAF,0x48,0xA0,0x3B,0xBF,0xD2,0x5E,0x8C,0xD0,0x36,0x41,0x41};
+            for (int k = 31; k >= 0; k--) {
+                int d = (int)order[k] - (int)sig[64 * i + 32 + k] - borrow;
+                borrow = d < 0; sig[64 * i + 32 + k] = (uint8_t)(d + (borrow << 8));
+            }
+            break; }
+        case 6: memcpy(xonly32 + 32 * i, xonly32 + 32 * j, 32); break;
+        case 7: memset(xonly32 + 32 * i, 0, 32); xonly32[32 * i + 31] = 5; break; /* x = 5 is not on the curve */
+        }
+        (void)fieldp;
+    }
+}
+
 /* ---- opaque libsecp256k1 structs for the drop-in tests (what CLN's wire parsers hand to check_signed_hash) ---- */
 int ref_make_opaque_pubkey(const uint8_t *pub33, uint8_t *opaque64) {
     secp256k1_pubkey pk;

@@ -10,6 +10,8 @@ exists; the GPU box only sees the generated files).  Vectors are data, not code:
   pubkey_parse.json       valid / invalid 33-byte encodings from tests.c run_ec_pubkey_parse_test (:5893-)
   gossip_subset.bin/.json a slice of tests/data/routing_gossip_store (real mainnet channel_announcement,
                           node_announcement, channel_update messages; all signatures valid under the reference)
+  routing_gossip_store    the reference's tests/data/routing_gossip_store itself (11,796 channel_announcements, 2,175
+                          node_announcements, 9,703 channel_updates), copied byte for byte for the full-size C4 replay
   chan_ann_3703.json      the mainnet channel_announcement of gossipd/test/run-check_channel_announcement.c
   ecmult_kat.json         the two digests of tests.c:5657-5726 (SHA-256 over x*G for derived scalars)
   ecdsa_edge_cases.json   the verification cases of test_ecdsa_edge_cases (tests.c:7069-7297): R = infinity, r = 0, s = 0,
@@ -222,6 +224,14 @@ def gossip():
     print("gossip subset:", nca, "CA,", nna, "NA,", ncu, "CU ->", n, "signatures, all valid;", len(blob), "bytes")
 
 
+def gossip_store_full():
+    """The whole fixture, byte for byte (7.6 MB): config C4 replays ALL of it (bench.py --config c4, tests/test_gpu_c4.py)."""
+    import shutil
+    shutil.copyfile(REF + "/tests/data/routing_gossip_store", OUT + "/routing_gossip_store")
+    msgs = parse_gossip_store(OUT + "/routing_gossip_store")
+    print("routing_gossip_store:", os.path.getsize(OUT + "/routing_gossip_store"), "bytes,", len(msgs), "records")
+
+
 def chan_ann_3703():
     src = open(REF + "/gossipd/test/run-check_channel_announcement.c").read()
     m = re.search(r'tal_hexdata\(\w+,\s*"([0-9a-f]+)"', src)
@@ -405,3 +415,4 @@ if __name__ == "__main__":
     ecmult_kat()
     ecdsa_edge_cases()
     bolt3_htlc_txs()
+    gossip_store_full()

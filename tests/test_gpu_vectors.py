@@ -279,3 +279,29 @@ def test_sigcheck_update_and_node_batches_and_init_shutdown(engine, cln):
     assert list(st) == want and want.count(1) > 10 and want.count(0) > 90
     lib.cln_sigverify_shutdown()
     lib.cln_sigverify_shutdown()  # idempotent
+
+
+def test_mixed_kinds_interleaved_config_c3(engine, ref):
+    """BASELINE config C3 in miniature: ECDSA (33-byte and x||y keys) and BIP-340 items interleaved by a seeded shuffle
+    with a kind tag per item, through sv_verify_mixed_host (device-side split per kind); every verdict vs the reference,
+    at sizes on both sides of the small-path threshold; an unknown tag gives verdict 0."""
+    w = util.corrupt(util.make_signed(ref, 9000, seed=31), every=6)
+    rng = np.random.default_rng(6)
+    for n in (1, 5, 64, 3000, 9000):
+        kinds = rng.choice([0, 0, 1, 2, 2], size=n).astype(np.uint8)
+        key = np.zeros((n, 64), np.uint8)
+        sig = np.zeros((n, 64), np.uint8)
+        want = np.zeros(n, np.uint8)
+        for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ssig")]):
+            sel = np.nonzero(kinds == kind)[0]
+            key[sel, :w[k].shape[1]] = w[k][:n][sel]
+            sig[sel] = w[s][:n][sel]
+            if sel.size:
+                want[sel] = util.ref_verify(ref, kind, np.ascontiguousarray(w["msg"][:n][sel]), np.ascontiguousarray(w[k][:n][sel]),
+                                            np.ascontiguousarray(w[s][:n][sel]), threads=4)
+        if n >= 64:
+            kinds[7] = 9  # not a kind
+            want[7] = 0
+        got = engine.verify_mixed(kinds, w["msg"][:n], key, sig)
+        assert np.array_equal(got, want), n
+    assert 0 < want.sum() < want.size
