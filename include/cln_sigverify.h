@@ -112,6 +112,13 @@ int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_l
 int sv_verify_gossip_host(sv_ctx *ctx, const uint8_t *blob, size_t blob_len, const uint64_t *msg_off,
                           const uint32_t *msg_len, size_t n_msgs, const uint8_t *cu_signers33, int *status);
 
+/* Key de-duplication: sv_verify_gossip_host looks for repeated keys in batches of >= 4096 signatures
+ * (exact hash table over the 33 key bytes, on the device); when at least 40 % of the items repeat a key, every DISTINCT
+ * key is decoded and its multiples table built once and the curve kernel indexes those tables.  Verdicts are unchanged.
+ * sv_set_dedup(ctx, 0) switches the search off; sv_last_distinct_keys reports what the last gossip batch contained. */
+int sv_set_dedup(sv_ctx *ctx, int on);
+unsigned sv_last_distinct_keys(const sv_ctx *ctx);
+
 /* ---- n ECDSA signatures by ONE key (every HTLC signature of a commitment_signed is made
  *      with remote_htlckey, channeld/channeld.c:2154,2215-2232).  The key is decoded and its multiples table built once;
  *      each verification skips the per-signature square root and table build.  kind: SV_KIND_ECDSA33 or _XY; key is

@@ -272,15 +272,58 @@ __global__ void k_sharedkey_build(int kind, const u8* key, sv_shared_key* out) {
 }
 __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main_shared(const sv_work* work, const u8* __restrict__ sig, size_t n, const ge_mem* __restrict__ gtab,
-                  const sv_shared_key* sk, u8* __restrict__ verdict) {
+                  const sv_shared_key* sk, const u32* __restrict__ sk_index, u8* __restrict__ verdict, u8* __restrict__ aux) {
+    // sk_index == nullptr: ONE key for the whole batch (channeld's HTLC loop); else item i uses table sk[sk_index[i]]
+    // (key de-duplication inside a gossip batch: every distinct key is decoded and tabulated once)
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += stride) {
         size_t i = base + threadIdx.x;
         bool active = i < n;
         const sv_work* w = active ? (work + i) : &g_idle_work;
-        u32 v = verify_curve_side_shared(w, sig + 64 * (active ? i : 0), gtab, sk, blockDim.x);
-        if (active) verdict[i] = (u8)v;
+        const sv_shared_key* k = sk_index ? (sk + sk_index[active ? i : 0]) : sk;
+        u32 v = verify_curve_side_shared(w, sig + 64 * (active ? i : 0), gtab, k, blockDim.x);
+        if (active) {
+            verdict[i] = (u8)v;
+            if (aux) aux[i] = (u8)((k->ok ? 1u : 0u) | ((w->flags & SV_WF_PARSED) ? 2u : 0u));
+        }
     }
+}
+
+// ---- key de-duplication (N3): exact (full 33-byte compare) open-addressing hash table keyed by the key bytes ----
+__global__ void __launch_bounds__(256) k_dedup_insert(const u8* __restrict__ key, int keylen, size_t n, u32* slots, u32 mask,
+                                                      u32* __restrict__ rep) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u8* k = key + (size_t)keylen * i;
+    u32 h = 2166136261u;
+    for (int b = 0; b < 12; b++) h = (h ^ k[b]) * 16777619u;  // FNV-1a over the prefix and the top of x
+    u32 slot = (h ^ (h >> 15)) & mask;
+    for (;;) {
+        u32 old = atomicCAS(&slots[slot], 0xFFFFFFFFu, (u32)i);
+        if (old == 0xFFFFFFFFu) { rep[i] = (u32)i; return; }
+        const u8* o = key + (size_t)keylen * old;
+        bool same = true;
+        for (int b = 0; b < keylen; b++) same = same && (o[b] == k[b]);
+        if (same) { rep[i] = old; return; }
+        slot = (slot + 1) & mask;
+    }
+}
+__global__ void __launch_bounds__(256) k_dedup_number(const u32* __restrict__ rep, size_t n, u32* counter, u32* __restrict__ tid,
+                                                      u32* __restrict__ replist) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || rep[i] != (u32)i) return;
+    u32 t = atomicAdd(counter, 1u);
+    tid[i] = t;
+    replist[t] = (u32)i;
+}
+__global__ void __launch_bounds__(256) k_dedup_resolve(const u32* __restrict__ rep, size_t n, u32* __restrict__ tid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && rep[i] != (u32)i) tid[i] = tid[rep[i]];
+}
+__global__ void __launch_bounds__(128) k_sharedkey_build_many(int kind, const u8* __restrict__ key, int keylen,
+                                                              const u32* __restrict__ replist, u32 distinct, sv_shared_key* out) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < distinct) sharedkey_build(out + t, kind, key + (size_t)keylen * replist[t]);
 }
 
 // ---- device-side BIP143: one thread per transaction input -> msg32 ----------------------
@@ -719,6 +762,11 @@ struct sv_ctx {
     // from this pinned, device-mapped staging block (no H2D/D2H copy commands, no allocation)
     size_t small_max, small_cap;
     u8* h_small;
+    // key de-duplication scratch (hash table + index lists) and the table array of the distinct keys, grow-only
+    u8 *dd_buf, *sk_buf;
+    size_t dd_cap, sk_cap;
+    int dedup;  // gossip batches: look for repeated keys (sv_set_dedup; default on)
+    u32 last_distinct;
     // growable device staging for the host-buffer entry points
     size_t cap;  // items
     u8 *d_msg, *d_key, *d_sig, *d_verdict;
@@ -836,6 +884,10 @@ extern "C" int sv_create(sv_ctx** out, int device) {
                                           ctx->slot[i].done = nullptr; ctx->slot[i].last_stream = nullptr; ctx->slot[i].used = 0; }
     ctx->next_slot = 0;
     ctx->h_small = nullptr;
+    ctx->dd_buf = ctx->sk_buf = nullptr;
+    ctx->dd_cap = ctx->sk_cap = 0;
+    ctx->dedup = 1;
+    ctx->last_distinct = 0;
     ctx->small_cap = SV_SMALL_CAP;
     ctx->small_max = SV_SMALL_MAX_DEFAULT;
     if (const char* e = getenv("SV_SMALL_MAX")) ctx->small_max = (size_t)strtoull(e, nullptr, 10);
@@ -894,6 +946,7 @@ extern "C" void sv_destroy(sv_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->d_gtab); cudaFree(ctx->d_bases); cudaFree(ctx->d_sink);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    cudaFree(ctx->dd_buf); cudaFree(ctx->sk_buf);
     for (int i = 0; i < SV_NSLOTS; i++) {
         cudaFree(ctx->slot[i].d_scratch);
         cudaFree(ctx->slot[i].d_work);
@@ -926,6 +979,66 @@ extern "C" int sv_get_info(const sv_ctx* ctx, sv_info* info) {
 
 // launch prep + main on device-resident SoA arrays.  *used (optional) receives the slot whose work records the launch
 // wrote (the gossip status kernel reads their flags afterwards, on the same stream).
+// ECDSA batch with repeated keys: returns 1 if it handled the batch (enough repetition to pay), 0 if the caller should take
+// the ordinary path, < 0 on error.  Synchronises the stream once (the number of distinct keys sizes the table array).
+static int launch_verify_dedup(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
+                               u8* d_verdict, cudaStream_t st, u8* d_aux, u32* distinct_out) {
+    if (kind == SV_KIND_SCHNORR || n < 4096 || n > 0x7FFFFFFFu) return 0;
+    const int keylen = (int)sv_key_size(kind);
+    u32 cap = 1;
+    while (cap < 2 * n) cap <<= 1;
+    size_t head = (size_t)cap * 4 + 3 * n * 4 + 64;  // [slots cap][rep n][tid n][replist n][counter]
+    if (head > ctx->dd_cap) {
+        CK(cudaDeviceSynchronize());
+        size_t want = ctx->dd_cap ? ctx->dd_cap : (1u << 20);
+        while (want < head) want *= 2;
+        cudaFree(ctx->dd_buf); ctx->dd_buf = nullptr; ctx->dd_cap = 0;
+        CK(cudaMalloc(&ctx->dd_buf, want));
+        ctx->dd_cap = want;
+    }
+    u32* slots = reinterpret_cast<u32*>(ctx->dd_buf);
+    u32 *rep = slots + cap, *tid = rep + n, *replist = tid + n, *counter = replist + n;
+    CK(cudaMemsetAsync(slots, 0xFF, (size_t)cap * 4, st));
+    CK(cudaMemsetAsync(counter, 0, 4, st));
+    unsigned gb = (unsigned)((n + 255) / 256);
+    k_dedup_insert<<<gb, 256, 0, st>>>(d_key, keylen, n, slots, cap - 1, rep);
+    k_dedup_number<<<gb, 256, 0, st>>>(rep, n, counter, tid, replist);
+    k_dedup_resolve<<<gb, 256, 0, st>>>(rep, n, tid);
+    ctx->launches += 3;
+    u32 distinct = 0;
+    CK(cudaMemcpyAsync(&distinct, counter, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (distinct_out) *distinct_out = distinct;
+    if ((size_t)distinct * 10 > n * 6) return 0;  // fewer than 40 % repeats: the per-thread tables are as cheap
+    size_t need_sk = (size_t)distinct * sizeof(sv_shared_key);
+    if (need_sk > ctx->sk_cap) {
+        CK(cudaDeviceSynchronize());
+        size_t want = ctx->sk_cap ? ctx->sk_cap : (1u << 20);
+        while (want < need_sk) want *= 2;
+        cudaFree(ctx->sk_buf); ctx->sk_buf = nullptr; ctx->sk_cap = 0;
+        CK(cudaMalloc(&ctx->sk_buf, want));
+        ctx->sk_cap = want;
+    }
+    sv_shared_key* sk = reinterpret_cast<sv_shared_key*>(ctx->sk_buf);
+    sv_ctx::slot_t* sl = nullptr;
+    int rc = acquire_slot(ctx, n, st, &sl);
+    if (rc) return rc;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
+    size_t threads = (n + SV_PREP_BATCH - 1) / SV_PREP_BATCH;
+    k_prep_inv<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_msg, d_sig, n, sl->d_work);
+    k_prep_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_msg, d_sig, n, sl->d_work);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
+    k_sharedkey_build_many<<<(distinct + 127) / 128, 128, 0, st>>>(kind, d_key, keylen, replist, distinct, sk);
+    size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
+    unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
+    k_main_shared<<<grid, SV_MAIN_BLOCK, 0, st>>>(sl->d_work, d_sig, n, ctx->d_gtab, sk, tid, d_verdict, d_aux);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    rc = release_slot(ctx, sl, st);
+    return rc ? rc : 1;
+}
+
 static int launch_small(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
                         u8* d_verdict, u8* d_aux, cudaStream_t st) {
     unsigned grid = (unsigned)((n + SV_SMALL_ITEMS - 1) / SV_SMALL_ITEMS);
@@ -1001,6 +1114,12 @@ extern "C" int sv_verify_device(sv_ctx* ctx, int kind, const void* d_msg32, cons
                          (u32*)d_bitmap, st);
 }
 
+extern "C" int sv_set_dedup(sv_ctx* ctx, int on) {
+    if (!ctx) return SV_ERR_ARG;
+    ctx->dedup = on ? 1 : 0;
+    return SV_OK;
+}
+extern "C" unsigned sv_last_distinct_keys(const sv_ctx* ctx) { return ctx ? ctx->last_distinct : 0; }
 extern "C" int sv_set_small_max(sv_ctx* ctx, size_t n) {
     if (!ctx) return SV_ERR_ARG;
     ctx->small_max = n < ctx->small_cap ? n : ctx->small_cap;
@@ -1237,7 +1356,11 @@ extern "C" int sv_verify_gossip_host(sv_ctx* ctx, const uint8_t* blob, size_t bl
     if (items) {
         k_sha256d<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(ctx->d_data, ctx->d_off, ctx->d_len, items, ctx->d_msg);
         ctx->launches += 1;
-        rc = launch_verify(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, nullptr, st, d_keyok);
+        // node keys repeat heavily inside a gossip batch (every channel of a node, its updates, its announcement)
+        rc = ctx->dedup ? launch_verify_dedup(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, st, d_keyok,
+                                              &ctx->last_distinct) : 0;
+        if (rc == 0) rc = launch_verify(ctx, SV_KIND_ECDSA33, ctx->d_msg, ctx->d_key, ctx->d_sig, items, ctx->d_verdict, nullptr, st, d_keyok);
+        else if (rc == 1) rc = SV_OK;
         if (rc == SV_OK) {
             k_gossip_status<<<gm, 128, 0, st>>>(ctx->d_data, d_moff, d_mlen, d_base, n_msgs, ctx->d_verdict, d_keyok, d_status);
             ctx->launches += 1;
@@ -1289,7 +1412,7 @@ extern "C" int sv_verify_samekey_host(sv_ctx* ctx, int kind, const uint8_t* key,
     ctx->launches += 1;
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
-    k_main_shared<<<grid, SV_MAIN_BLOCK, 0, st>>>(sl->d_work, ctx->d_sig, n, ctx->d_gtab, d_sk, ctx->d_verdict);
+    k_main_shared<<<grid, SV_MAIN_BLOCK, 0, st>>>(sl->d_work, ctx->d_sig, n, ctx->d_gtab, d_sk, nullptr, ctx->d_verdict, nullptr);
     ctx->launches += 3;
     cudaError_t ce = cudaGetLastError();
     if (ce == cudaSuccess) ce = cudaEventRecord(sl->done, st);

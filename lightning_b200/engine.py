@@ -77,6 +77,9 @@ def load_library():
     lib.sv_selftest_host.argtypes = [vp, i, vp, vp, sz, vp]
     lib.sv_verify_mixed_host.argtypes = [vp, vp, vp, vp, vp, sz, vp]
     lib.sv_verify_mixed_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]
+    lib.sv_set_dedup.argtypes = [vp, i]
+    lib.sv_last_distinct_keys.argtypes = [vp]
+    lib.sv_last_distinct_keys.restype = ctypes.c_uint
     lib.sv_set_small_max.argtypes = [vp, sz]
     lib.sv_get_small_max.argtypes = [vp]
     lib.sv_get_small_max.restype = sz
@@ -237,6 +240,12 @@ class SigVerifier:
         self._check(self.lib.sv_verify_mixed_host(self._ctx, kinds.ctypes.data, msg32.ctypes.data, key64.ctypes.data,
                                                   sig64.ctypes.data, n, out.ctypes.data), "sv_verify_mixed_host")
         return out[:n]
+
+    def set_dedup(self, on=True):
+        self._check(self.lib.sv_set_dedup(self._ctx, 1 if on else 0), "sv_set_dedup")
+
+    def last_distinct_keys(self):
+        return self.lib.sv_last_distinct_keys(self._ctx)
 
     def set_small_max(self, n):
         """largest batch that takes the small-batch (latency) path; 0 = always the throughput kernels"""

@@ -305,3 +305,56 @@ def test_mixed_kinds_interleaved_config_c3(engine, ref):
         got = engine.verify_mixed(kinds, w["msg"][:n], key, sig)
         assert np.array_equal(got, want), n
     assert 0 < want.sum() < want.size
+
+
+def test_gossip_key_deduplication_same_status(engine, cln):
+    """Row N3: a gossip batch repeats node keys heavily; with de-duplication every distinct key is decoded and tabulated once.
+    Per-message status must be identical with the search on and off, and equal to gossipd's on a sample; corrupted keys
+    (undecodable, flipped) and corrupted signatures included."""
+    import struct
+    msgs = gossip.load_subset()
+    chans = {}
+    for m in msgs:
+        if m[:2] == b"\x01\x00":
+            flen = struct.unpack(">H", m[258:260])[0]
+            p = 260 + flen + 32
+            chans[m[p:p + 8]] = (m[p + 8:p + 41], m[p + 41:p + 74])
+    sel = [m for m in msgs if m[:2] in (b"\x01\x00", b"\x01\x01")] + [m for m in msgs if m[:2] == b"\x01\x02" and m[98:106] in chans]
+    sel = sel * 3
+    rng = np.random.default_rng(21)
+    batch = []
+    for m in sel:
+        b = bytearray(m)
+        if rng.random() < 0.05:
+            while True:
+                pos = int(rng.integers(2, len(b)))
+                if pos not in (66, 67, 258, 259):
+                    break
+            b[pos] ^= 1 << int(rng.integers(0, 8))
+        batch.append(bytes(b))
+    signers = np.zeros((len(batch), 33), np.uint8)
+    for i, m in enumerate(batch):
+        if m[:2] == b"\x01\x02":
+            ends = chans.get(bytes(m[98:106]))
+            if ends:
+                signers[i] = np.frombuffer(ends[m[111] & 1], dtype=np.uint8)
+    engine.set_dedup(True)
+    a = engine.verify_gossip(batch, signers).copy()
+    distinct = engine.last_distinct_keys()
+    engine.set_dedup(False)
+    b = engine.verify_gossip(batch, signers).copy()
+    engine.set_dedup(True)
+    assert np.array_equal(a, b)
+    items = sum(4 if m[:2] == b"\x01\x00" else 1 for m in batch)
+    assert items > 15000 and 0 < distinct < 0.6 * items, (items, distinct)
+    for i in rng.choice(len(batch), size=400, replace=False):
+        m = batch[i]
+        L_ = ctypes.c_size_t(len(m))
+        if m[:2] == b"\x01\x00":
+            want = cln.cln_sigcheck_channel_announcement(m, L_)
+        elif m[:2] == b"\x01\x01":
+            want = cln.cln_sigcheck_node_announcement(m, L_)
+        else:
+            want = cln.cln_sigcheck_channel_update(m, L_, P(np.ascontiguousarray(signers[i])))
+        assert a[i] == want, (i, a[i], want)
+    assert (a == 0).sum() > 0.8 * len(batch) and (a != 0).sum() > 100
