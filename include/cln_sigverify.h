@@ -211,7 +211,9 @@ enum {
     SV_ST_SC_SET_B32 = 27,    /* a = 32 big-endian bytes: reduced scalar, out[8] = overflow */
     SV_ST_ECMULT_GEN = 28,    /* a*G through the fixed-base comb table: affine x -> out[0..7], y -> out[8..15]; 0 -> zeros */
     SV_ST_PREPARE_U2 = 29,    /* b = u2: |k1| -> out[0..4], |k2| -> out[5..9] (sign in bit 159), both odd */
-    SV_ST_PREPARE_U1 = 30     /* a = u1: 16 signed comb digits -> out[0..15] */
+    SV_ST_PREPARE_U1 = 30,    /* a = u1: 16 signed comb digits -> out[0..15] */
+    SV_ST_SC_INVERSE_VAR = 31, /* binary extended Euclid: same value as SV_ST_SC_INVERSE */
+    SV_ST_FE_INV_VAR = 32     /* canonical 1/a mod p */
 };
 int sv_selftest_host(sv_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, size_t n, uint32_t *out);
 

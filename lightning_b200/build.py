@@ -42,9 +42,13 @@ def _sources(d, exts):
 
 
 def build_engine(force=False, verbose=False, extra_flags=()):
-    srcs = _sources(CSRC, (".cu", ".cuh", ".c")) + [os.path.join(ROOT, "include", "cln_sigverify.h"),
+    srcs = _sources(CSRC, (".cu", ".cuh", ".c", ".h")) + [os.path.join(ROOT, "include", "cln_sigverify.h"),
                                                    os.path.join(ROOT, "include", "cln_dropin.h")]
-    if not force and _newer(LIB, srcs):
+    # the flags are part of what the library is: a change of flags (or extra_flags) must rebuild, and so must a stale daemon
+    stamp = os.path.join(os.path.dirname(LIB), ".build_flags")
+    flags_now = " ".join(NVCC_FLAGS + list(extra_flags))
+    same_flags = os.path.exists(stamp) and open(stamp).read() == flags_now
+    if not force and same_flags and _newer(LIB, srcs) and _newer(DAEMON, srcs):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     # host side of the drop-in is plain C (as the reference's bitcoin/signature.c), compiled by gcc
@@ -65,6 +69,7 @@ def build_engine(force=False, verbose=False, extra_flags=()):
                         "-L" + os.path.dirname(LIB), "-lcln_sigverify", "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("gcc (sigverifyd.c) failed:\n" + r.stdout + r.stderr)
+    open(stamp, "w").write(flags_now)
     return LIB
 
 

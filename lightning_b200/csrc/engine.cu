@@ -1608,7 +1608,7 @@ extern "C" int sv_flush(sv_ctx* ctx, uint8_t* verdicts, size_t capacity) {
 
 // ---- self test (test support) ---------------------------------------------------------------------
 extern "C" int sv_selftest_host(sv_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
-    if (!ctx || op < 0 || op > SV_ST_PREPARE_U1 || (n && (!a || !b || !out))) return SV_ERR_ARG;
+    if (!ctx || op < 0 || op > SV_ST_FE_INV_VAR || (n && (!a || !b || !out))) return SV_ERR_ARG;
     if (n == 0) return SV_OK;
     dev_guard dg__;
     CK(dg__.enter(ctx->device));

@@ -593,6 +593,14 @@ SV_HD void fe_inv(fe& r, const fe& a) {
     fe_mul(r, t, a);
 }
 
+// 1/a by binary extended Euclid (variable time; 0 -> 0; result canonical): see u256_modinv_var
+SV_HD void fe_inv_var(fe& r, const fe& a) {
+    const u32 P[8] = {SV_P0, SV_P1, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    fe t = a;
+    fe_normalize(t);
+    u256_modinv_var(r.v, t.v, P);
+}
+
 // big-endian 32 bytes -> limbs; returns false if value >= p (reference: secp256k1_fe_set_b32_limit,
 // field_5x52_impl.h:272)
 SV_HD bool fe_set_b32(fe& r, const u8* b) {

@@ -238,6 +238,10 @@ SV_HD void sc_inverse(sc& r, const sc& a) {
     r = acc;
 }
 
+// 1/a mod n by binary extended Euclid (variable time; 0 -> 0): the inversion of ONE scalar on the critical path of the
+// small-batch kernel.  Same value as sc_inverse.
+SV_HD void sc_inverse_var(sc& r, const sc& a) { u256_modinv_var(r.v, a.v, SC_N); }
+
 // (a*b) >> 384 rounded to nearest: reference secp256k1_scalar_mul_shift_var (scalar_4x64_impl.h:1049)
 SV_HD void sc_mul_shift384(sc& r, const sc& a, const u32 b[8]) {
     u32 t[16];

@@ -57,6 +57,8 @@ SV_UNROLL
         case SV_ST_SC_ADD: sc_add(s, p, q); is_sc = true; break;
         case SV_ST_SC_NEGATE: sc_negate(s, p); is_sc = true; R[8] = sc_is_high(p); R[9] = sc_is_zero(p); R[10] = sc_gte_n(A); break;
         case SV_ST_SC_INVERSE: sc_inverse(s, p); is_sc = true; break;
+        case SV_ST_SC_INVERSE_VAR: sc_inverse_var(s, p); is_sc = true; break;
+        case SV_ST_FE_INV_VAR: fe_inv_var(r, x); is_fe = true; break;
         case SV_ST_SC_REDUCE512: {
             u32 t[16];
 SV_UNROLL

@@ -341,3 +341,47 @@ SV_HD void u256_sqr_wide(u32 r[16], const u32 a[8]) {
     u256_mul_wide_schoolbook(r, a, a);
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------
+// a^-1 mod m for an odd modulus m (a < m; 0 -> 0), variable time: binary extended Euclid with the invariants
+// x1*a == u and x2*a == v (mod m).  Every pass halves u (after making it even by subtracting the smaller of u, v), so the
+// loop ends within bits(u) + bits(v) <= 512 passes.  Used where ONE inversion sits on the critical path of a lone
+// verification (small-batch path): ~500 short passes instead of the ~330 dependent multiplications of a Fermat chain.
+// The reference inverts with safegcd (modinv64_impl.h:638), also variable time in the verification path.
+// ---------------------------------------------------------------------------------------------
+SV_HD void u256_shr1(u32 r[8], u32 top) {  // r = (top:r) >> 1
+    SV_UNROLL
+    for (int i = 0; i < 7; i++) r[i] = (r[i] >> 1) | (r[i + 1] << 31);
+    r[7] = (r[7] >> 1) | (top << 31);
+}
+SV_HD void u256_modinv_var(u32 r[8], const u32 a[8], const u32 m[8]) {
+    u32 u[8], v[8], x1[8], x2[8];
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) { u[i] = a[i]; v[i] = m[i]; x1[i] = (i == 0); x2[i] = 0; }
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int it = 0; it < 520; it++) {
+        if (u256_is_zero(u)) break;
+        if (u[0] & 1u) {
+            u32 t[8];
+            u32 lt = u256_sub(t, u, v);  // borrow <=> u < v
+            if (lt) {                    // swap the pairs, then u - v is v_old - u_old = -t
+                SV_UNROLL
+                for (int i = 0; i < 8; i++) { u32 w = u[i]; u[i] = v[i]; v[i] = w; w = x1[i]; x1[i] = x2[i]; x2[i] = w; }
+                (void)u256_sub(u, u, v);
+            } else {
+                SV_UNROLL
+                for (int i = 0; i < 8; i++) u[i] = t[i];
+            }
+            u32 bw = u256_sub(x1, x1, x2);  // x1 = x1 - x2 mod m
+            if (bw) (void)u256_add(x1, x1, m);
+        }
+        u256_shr1(u, 0);
+        u32 c = 0;
+        if (x1[0] & 1u) c = u256_add(x1, x1, m);  // make x1 even (m is odd), keeping the 257th bit
+        u256_shr1(x1, c);
+    }
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = x2[i];
+}

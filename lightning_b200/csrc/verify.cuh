@@ -410,11 +410,11 @@ SV_HD u32 ecdsa_final(const gej& R, const u8* sig64, u32 flags) {
 }
 
 // final comparison, BIP-340: R finite, y(R) even, x(R) == r  (main_impl.h:255-264)
-SV_HD u32 schnorr_final(const gej& R, const u8* sig64) {
+SV_HD u32 schnorr_final(const gej& R, const u8* sig64, bool var_time_inverse = false) {
     if (R.inf) return 0;
     fe zi, rx;
     ge a;
-    fe_inv(zi, R.z);
+    if (var_time_inverse) fe_inv_var(zi, R.z); else fe_inv(zi, R.z);
     ge_set_gej_zinv(a, R, zi);
     fe_normalize(a.y);
     if (fe_is_odd(a.y)) return 0;
@@ -559,7 +559,7 @@ SV_HD void small_scalar_side(int kind, const u8* msg32, const u8* key, const u8*
         SV_UNROLL
         for (int k = 0; k < 8; k++) s.v[k] = (k == 0);
     }
-    sc_inverse(sinv, s);
+    sc_inverse_var(sinv, s);
     ecdsa_finish_prep(it->w, ok, r, m, sinv, parsed);
 }
 // one GLV half: R = (+-|k|) * Q (or lambda*Q) on the scaled curve, 33 regular signed-odd-digit windows
@@ -634,7 +634,7 @@ SV_HD u32 small_finish(int kind, sv_small_item* it, const u8* sig64, bool* key_o
     u32 flags = it->w.flags;
     bool ok = (flags & SV_WF_VALID) != 0 && it->key_ok != 0;
     if (key_ok) *key_ok = it->key_ok != 0;
-    u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);
+    u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64, true) : ecdsa_final(R, sig64, flags);
     return ok ? v : 0u;
 }
 // the three phases run one after another (host build of the kernel source, tests/host_emul)

@@ -24,7 +24,7 @@ P, N = M.P, M.N
 OPS = dict(FE_MUL=0, FE_SQR=1, FE_ADD=2, FE_SUB=3, FE_NEG=4, FE_NORMALIZE=5, FE_INV=6, FE_SQRT=7, FE_MUL3=8, FE_MUL8=9,
            FE_MUL_SMALL=10, FE_DBL=11, FE_B32=12, U256_MUL_WIDE=13, U256_SQR_WIDE=14, FE_REDUCE512=15, U256_ADD=16,
            U256_SUB=17, SC_MUL=20, SC_SQR=21, SC_ADD=22, SC_NEGATE=23, SC_INVERSE=24, SC_REDUCE512=25, SC_SPLIT_LAMBDA=26,
-           SC_SET_B32=27, ECMULT_GEN=28, PREPARE_U2=29, PREPARE_U1=30)
+           SC_SET_B32=27, ECMULT_GEN=28, PREPARE_U2=29, PREPARE_U1=30, SC_INVERSE_VAR=31, FE_INV_VAR=32)
 COVERAGE = {}
 
 
@@ -244,6 +244,15 @@ def case_scalar_ops_edge_and_rare_folds(engine):
         assert g == (-a) % N and int(fl[8]) == (a > (N - 1) // 2) and int(fl[9]) == (a == 0) and int(fl[10]) == 0
     for g, a in zip(ints(run2(engine, "SC_INVERSE", E, Z)), E):
         assert g == pow(a, N - 2, N)
+    # the variable-time inverses of the small-batch path (binary extended Euclid): edge values, powers of two and their
+    # neighbours (long shift runs), random values
+    inv_in = E + [2**k for k in range(1, 256, 7)] + [2**k - 1 for k in range(2, 256, 11)] + [N - 2**k for k in range(1, 250, 13)] + \
+        [rnd.randrange(1, N) for _ in range(1500)]
+    for g, a in zip(ints(run2(engine, "SC_INVERSE_VAR", inv_in, [0] * len(inv_in))), inv_in):
+        assert g == pow(a, N - 2, N), hex(a)
+    fin = [v for v in M.EDGE_FE] + [2**k for k in range(1, 256, 9)] + [P - 2**k for k in range(1, 250, 17)] + [rnd.getrandbits(256) for _ in range(1500)]
+    for g, a in zip(ints(run2(engine, "FE_INV_VAR", fin, [0] * len(fin))), fin):
+        assert g == pow(a % P, P - 2, P), hex(a)
     # the carry of the third fold, reached directly and through products of reduced scalars
     ts = [M.sc_fold4_t(rnd) for _ in range(3000)] + [2**512 - 1, 0, 2**256, N * N, (N - 1) ** 2, 2**512 - 2**256, N << 256] + \
          [rnd.getrandbits(512) for _ in range(3000)]

@@ -389,10 +389,15 @@ def test_samekey_batch(engine, ref):
     assert not engine.verify_samekey(0, bad, msg, sig).any()
 
 
-def test_verifier_subdaemon(ref, tmp_path):
-    """Row N4: one GPU-owning process serving several clients over a unix socket (CLN-style framed requests)."""
-    import socket, struct, subprocess, time
+def test_verifier_subdaemon(ref, cln, tmp_path):
+    """Row N4: one GPU-owning process serving many clients over a unix socket with CLN-style framing (wire CSV codec),
+    coalescing the requests of ALL clients into shared launches: 8 clients x 40 requests in flight, every verdict vs the
+    reference; the daemon's own counters must show fewer launches than requests; gossip requests, malformed requests
+    (answered with sigverifyd_error, connection kept), an absurd length prefix (connection closed, the others unaffected),
+    socket mode 0600, and the inherited-fd mode lightningd would use."""
+    import socket, stat, struct, subprocess, threading, time
     from lightning_b200 import build
+    from lightning_b200 import sigverifyd_wire as W
     sock_path = str(tmp_path / "sv.sock")
     proc = subprocess.Popen([build.DAEMON, sock_path, "0"], stderr=subprocess.PIPE)
     try:
@@ -401,32 +406,90 @@ def test_verifier_subdaemon(ref, tmp_path):
                 break
             time.sleep(0.1)
         assert os.path.exists(sock_path), "daemon did not come up"
-        w = util.corrupt(util.make_signed(ref, 900, seed=21), every=6)
-        clients = [socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) for _ in range(3)]
-        for c in clients:
-            c.connect(sock_path)
-        reqs = [(0, "pub33", "sig", slice(0, 300)), (1, "pubxy", "sig", slice(300, 600)), (2, "xonly", "ssig", slice(600, 900))]
-        for c, (kind, k, s, sl) in zip(clients, reqs):  # all three requests in flight before any reply is read
-            body = bytes([kind]) + struct.pack(">I", 300) + w["msg"][sl].tobytes() + w[k][sl].tobytes() + w[s][sl].tobytes()
-            c.sendall(struct.pack(">I", len(body)) + body)
-        for c, (kind, k, s, sl) in zip(clients, reqs):
-            def rd(n):
-                b = b""
-                while len(b) < n:
-                    chunk = c.recv(n - len(b))
-                    assert chunk
-                    b += chunk
-                return b
-            ln = struct.unpack(">I", rd(4))[0]
-            payload = rd(ln)
-            assert struct.unpack(">I", payload[:4])[0] == 300
-            got = np.frombuffer(payload[4:], dtype=np.uint8)
-            want = util.ref_verify(ref, kind, w["msg"][sl], w[k][sl], w[s][sl])
-            assert np.array_equal(got, want), kind
-        clients[0].sendall(struct.pack(">I", 5) + bytes([9]) + struct.pack(">I", 0))  # bad kind: connection dropped
-        assert clients[0].recv(4) == b""
-        for c in clients:
-            c.close()
+        assert stat.S_IMODE(os.stat(sock_path).st_mode) == 0o600
+        w = util.corrupt(util.make_signed(ref, 2400, seed=21), every=6)
+        kinds = [(0, "pub33", "sig", 33), (1, "pubxy", "sig", 64), (2, "xonly", "ssig", 32)]
+        want = [util.ref_verify(ref, k, w["msg"], w[kk], w[ss]) for k, kk, ss, _ in kinds]
+        errors = []
+
+        def client(ci):
+            try:
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.connect(sock_path)
+                reqs = []
+                for j in range(40):  # all requests of this client are sent before any reply is read
+                    kind, kk, ss, ks = kinds[(ci + j) % 3]
+                    lo = (ci * 40 + j) * 7 % 2300
+                    n = 1 + (ci + j) % 60
+                    sl = slice(lo, lo + n)
+                    c.sendall(W.encode("sigverifyd_verify", req_id=ci * 1000 + j, kind=kind, n=n, hashes=w["msg"][sl].tobytes(),
+                                       keylen=n * ks, keys=w[kk][sl].tobytes(), sigs=w[ss][sl].tobytes()))
+                    reqs.append((ci * 1000 + j, kind, sl))
+                got = {}
+                for _ in reqs:
+                    name, v = W.read_msg(c)
+                    assert name == "sigverifyd_verify_reply", name
+                    got[v["req_id"]] = v
+                for rid, kind, sl in reqs:
+                    assert np.array_equal(np.frombuffer(got[rid]["verdicts"], dtype=np.uint8), want[kind][sl]), (rid, kind)
+                c.close()
+            except Exception as ex:  # noqa: BLE001
+                errors.append((ci, repr(ex)))
+        th = [threading.Thread(target=client, args=(i,)) for i in range(8)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=120)
+        assert not errors, errors
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.connect(sock_path)
+        c.sendall(W.encode("sigverifyd_stats", req_id=5))
+        name, st = W.read_msg(c)
+        assert name == "sigverifyd_stats_reply" and st["requests"] == 320
+        assert st["launches"] < st["requests"] and st["max_coalesced"] >= 2, st  # requests of different clients shared launches
+        # malformed requests are answered, not fatal: bad kind, key bytes that do not match n
+        c.sendall(W.encode("sigverifyd_verify", req_id=77, kind=9, n=0, hashes=b"", keylen=0, keys=b"", sigs=b""))
+        assert W.read_msg(c) == ("sigverifyd_error", dict(req_id=77, code=1))
+        c.sendall(W.encode("sigverifyd_verify", req_id=78, kind=0, n=1, hashes=bytes(32), keylen=32, keys=bytes(32), sigs=bytes(64)))
+        assert W.read_msg(c) == ("sigverifyd_error", dict(req_id=78, code=1))
+        # a gossip request: raw messages in, status per message out (255 = malformed), vs gossipd/sigcheck.c
+        msgs = [m for m in gossip.load_subset() if m[:2] in (b"\x01\x00", b"\x01\x01")][:60]
+        msgs[3] = msgs[3][:2] + bytes([msgs[3][2] ^ 1]) + msgs[3][3:]
+        msgs[9] = msgs[9][:100]
+        c.sendall(W.encode("sigverifyd_gossip", req_id=6, n=len(msgs), lens=[len(m) for m in msgs], signers=bytes(33 * len(msgs)),
+                           bloblen=sum(len(m) for m in msgs), blob=b"".join(msgs)))
+        name, g = W.read_msg(c)
+        ref_status = []
+        for m in msgs:
+            L_ = ctypes.c_size_t(len(m))
+            r = cln.cln_sigcheck_channel_announcement(m, L_) if m[:2] == b"\x01\x00" else cln.cln_sigcheck_node_announcement(m, L_)
+            ref_status.append(255 if r < 0 else r)
+        assert name == "sigverifyd_gossip_reply" and list(g["status"]) == ref_status
+        # an absurd length prefix closes THAT connection; the daemon keeps serving the others
+        bad = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        bad.connect(sock_path)
+        bad.sendall(struct.pack(">I", 0xFFFFFFF0) + b"xx")
+        assert bad.recv(4) == b""
+        c.sendall(W.encode("sigverifyd_stats", req_id=8))
+        assert W.read_msg(c)[0] == "sigverifyd_stats_reply"
+        c.close()
     finally:
         proc.terminate()
         proc.wait(timeout=10)
+    # inherited-fd mode: one end of a socketpair handed to the child, as lightningd does for its subdaemons
+    a, b = socket.socketpair(socket.AF_UNIX, socket.SOCK_STREAM)
+    proc = subprocess.Popen([build.DAEMON, "--fd", str(b.fileno()), "0"], pass_fds=[b.fileno()], stderr=subprocess.PIPE)
+    b.close()
+    try:
+        a.settimeout(120)
+        sl = slice(0, 5)
+        a.sendall(W.encode("sigverifyd_verify", req_id=1, kind=0, n=5, hashes=w["msg"][sl].tobytes(), keylen=165,
+                           keys=w["pub33"][sl].tobytes(), sigs=w["sig"][sl].tobytes()))
+        name, v = W.read_msg(a)
+        assert name == "sigverifyd_verify_reply" and np.array_equal(np.frombuffer(v["verdicts"], dtype=np.uint8), want[0][sl])
+        a.close()
+        assert proc.wait(timeout=30) == 0  # the parent went away: the daemon exits by itself
+    finally:
+        if proc.poll() is None:
+            proc.terminate()
+            proc.wait(timeout=10)
