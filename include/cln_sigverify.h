@@ -112,6 +112,11 @@ int sv_verify_host_raw(sv_ctx *ctx, int kind, const uint8_t *data, size_t data_l
 int sv_verify_gossip_host(sv_ctx *ctx, const uint8_t *blob, size_t blob_len, const uint64_t *msg_off,
                           const uint32_t *msg_len, size_t n_msgs, const uint8_t *cu_signers33, int *status);
 
+/* L2 residency hint for the throughput kernels (default on): the G comb table and the per-thread multiples tables are
+ * marked persisting through a stream access-policy window, the rest of the stream's traffic streaming.  0 switches it off
+ * for streams not yet seen (measurement aid). */
+int sv_set_l2_policy(sv_ctx *ctx, int on);
+
 /* Key de-duplication: sv_verify_gossip_host looks for repeated keys in batches of >= 4096 signatures
  * (exact hash table over the 33 key bytes, on the device); when at least 40 % of the items repeat a key, every DISTINCT
  * key is decoded and its multiples table built once and the curve kernel indexes those tables.  Verdicts are unchanged.
