@@ -117,6 +117,16 @@ int sv_verify_gossip_host(sv_ctx *ctx, const uint8_t *blob, size_t blob_len, con
  * for streams not yet seen (measurement aid). */
 int sv_set_l2_policy(sv_ctx *ctx, int on);
 
+/* ---- BIP-340 BATCH verification by random linear combination (BIP-340 "Batch Verification").  The batch
+ *      is cut into groups of 1024 signatures; each group's equation  sum a_i R_i + sum a_i e_i P_i - (sum a_i s_i) G = 0
+ *      is evaluated with a per-warp bucket method (about half the field work of one-by-one verification); the members of
+ *      a group whose equation fails are re-verified one by one, so every verdict is the one sv_verify_host(SV_KIND_SCHNORR)
+ *      gives, up to the 2^-127 chance that random a_i hide a bad signature.  Meant for batches that are almost all valid
+ *      (a bad signature costs its whole group the fast path).  seed32: 32 bytes the signers could not predict (NULL: taken
+ *      from getrandom()).  groups_total / groups_failed (optional) report how the batch went. ---- */
+int sv_verify_schnorr_batch_host(sv_ctx *ctx, const uint8_t *msg32, const uint8_t *xonly32, const uint8_t *sig64, size_t n,
+                                 const uint8_t *seed32, uint8_t *verdicts, uint32_t *groups_total, uint32_t *groups_failed);
+
 /* Key de-duplication: sv_verify_gossip_host looks for repeated keys in batches of >= 4096 signatures
  * (exact hash table over the 33 key bytes, on the device); when at least 40 % of the items repeat a key, every DISTINCT
  * key is decoded and its multiples table built once and the curve kernel indexes those tables.  Verdicts are unchanged.

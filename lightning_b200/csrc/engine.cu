@@ -1729,6 +1729,96 @@ extern "C" int sv_verify_mixed_host(sv_ctx* ctx, const uint8_t* kinds, const uin
     return SV_OK;
 }
 
+// ---- BIP-340 batch verification, host entry (batch.cuh) --------------------------------------------------------------
+#include <sys/random.h>
+extern "C" int sv_verify_schnorr_batch_host(sv_ctx* ctx, const uint8_t* msg32, const uint8_t* xonly32, const uint8_t* sig64,
+                                            size_t n, const uint8_t* seed32, uint8_t* verdicts, uint32_t* groups_total,
+                                            uint32_t* groups_failed) {
+    if (!ctx || (n && (!msg32 || !xonly32 || !sig64 || !verdicts))) return SV_ERR_ARG;
+    if (groups_total) *groups_total = 0;
+    if (groups_failed) *groups_failed = 0;
+    if (n == 0) return SV_OK;
+    if (n > 0x7FFFFFFFu) return SV_ERR_ARG;
+    dev_guard dg__;
+    CK(dg__.enter(ctx->device));
+    uint8_t seed[32];
+    if (seed32) memcpy(seed, seed32, 32);
+    else if (getrandom(seed, 32, 0) != 32) return fail(ctx, SV_ERR_ARG, "getrandom", cudaSuccess);
+    int rc = ensure_staging(ctx, n);
+    if (rc) return rc;
+    const u32 groups = (u32)((n + SV_SB_GROUP - 1) / SV_SB_GROUP);
+    // scratch: [seed 32][pts 2n x 96][t n x 32][S groups x W x 128][dig W x 4n][ok n][group_ok groups][out n][idx n x 4]
+    size_t o_pts = 64, o_t = o_pts + 2 * n * sizeof(qtab_entry), o_S = o_t + n * sizeof(sc),
+           o_dig = o_S + (size_t)groups * SV_SB_WINDOWS * sizeof(sv_jac), o_ok = (o_dig + (size_t)SV_SB_WINDOWS * 4 * n + 15) & ~(size_t)15,
+           o_gok = (o_ok + n + 15) & ~(size_t)15, o_out = (o_gok + groups + 15) & ~(size_t)15, o_idx = (o_out + n + 15) & ~(size_t)15,
+           need = o_idx + 4 * n + 64;
+    if (need > ctx->dd_cap) {
+        CK(cudaDeviceSynchronize());
+        size_t want = ctx->dd_cap ? ctx->dd_cap : (1u << 20);
+        while (want < need) want *= 2;
+        cudaFree(ctx->dd_buf); ctx->dd_buf = nullptr; ctx->dd_cap = 0;
+        CK(cudaMalloc(&ctx->dd_buf, want));
+        ctx->dd_cap = want;
+    }
+    u8* B = ctx->dd_buf;
+    qtab_entry* d_pts = reinterpret_cast<qtab_entry*>(B + o_pts);
+    sc* d_t = reinterpret_cast<sc*>(B + o_t);
+    sv_jac* d_S = reinterpret_cast<sv_jac*>(B + o_S);
+    signed char* d_dig = reinterpret_cast<signed char*>(B + o_dig);
+    u8 *d_ok = B + o_ok, *d_gok = B + o_gok, *d_out = B + o_out;
+    u32* d_idx = reinterpret_cast<u32*>(B + o_idx);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(B, seed, 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_msg, msg32, 32 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_key, xonly32, 32 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_sig, sig64, 64 * n, cudaMemcpyHostToDevice, st));
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
+    k_sb_prep<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_msg, ctx->d_key, ctx->d_sig, n, B, d_pts, d_dig, d_t, d_ok);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
+    u32 jobs = groups * SV_SB_WINDOWS;
+    k_sb_window<<<(jobs + SV_SB_WARPS - 1) / SV_SB_WARPS, 32 * SV_SB_WARPS, 0, st>>>(d_pts, d_dig, n, groups, d_S);
+    k_sb_final<<<(groups + 63) / 64, 64, 0, st>>>(d_S, d_t, n, groups, ctx->d_gtab, d_gok);
+    k_sb_verdicts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ok, d_gok, n, d_out);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    std::vector<u8> gok(groups), ok(n);
+    CK(cudaMemcpyAsync(gok.data(), d_gok, groups, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ok.data(), d_ok, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // members of failed groups (whose encoding is fine) go through one-by-one verification; their verdicts replace the zeros
+    std::vector<u32> idx;
+    u32 failed = 0;
+    for (u32 g = 0; g < groups; g++) {
+        if (gok[g]) continue;
+        failed++;
+        size_t lo = (size_t)g * SV_SB_GROUP, hi = lo + SV_SB_GROUP < n ? lo + SV_SB_GROUP : n;
+        for (size_t i = lo; i < hi; i++)
+            if (ok[i]) idx.push_back((u32)i);
+    }
+    if (groups_total) *groups_total = groups;
+    if (groups_failed) *groups_failed = failed;
+    if (!idx.empty()) {
+        size_t c = idx.size();
+        CK(cudaMemcpyAsync(d_idx, idx.data(), 4 * c, cudaMemcpyHostToDevice, st));
+        // gathered copies live in the upper halves... of a second staging area: the pts array is dead by now (2n x 96 bytes >= 160 c)
+        u8* g_msg = reinterpret_cast<u8*>(d_pts);
+        u8* g_key = g_msg + 32 * c;
+        u8* g_sig = g_key + 32 * c;
+        u8* g_v = g_sig + 64 * c;
+        k_sb_gather<<<(unsigned)((c + 255) / 256), 256, 0, st>>>(d_idx, c, ctx->d_msg, ctx->d_key, ctx->d_sig, g_msg, g_key, g_sig);
+        ctx->launches += 1;
+        rc = launch_verify(ctx, SV_KIND_SCHNORR, g_msg, g_key, g_sig, c, g_v, nullptr, st);
+        if (rc) return rc;
+        k_mixed_scatter<<<(unsigned)((c + 255) / 256), 256, 0, st>>>(d_idx, c, g_v, d_out);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(verdicts, d_out, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SV_OK;
+}
+
 // ---- deferral queue -----------------------------------------------------------------------------
 extern "C" long sv_enqueue(sv_ctx* ctx, int kind, const uint8_t msg32[32], const uint8_t* key, const uint8_t sig64[64]) {
     size_t ks = sv_key_size(kind);

@@ -77,6 +77,7 @@ def load_library():
     lib.sv_selftest_host.argtypes = [vp, i, vp, vp, sz, vp]
     lib.sv_verify_mixed_host.argtypes = [vp, vp, vp, vp, vp, sz, vp]
     lib.sv_verify_mixed_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]
+    lib.sv_verify_schnorr_batch_host.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp]
     lib.sv_set_dedup.argtypes = [vp, i]
     lib.sv_last_distinct_keys.argtypes = [vp]
     lib.sv_last_distinct_keys.restype = ctypes.c_uint
@@ -240,6 +241,19 @@ class SigVerifier:
         self._check(self.lib.sv_verify_mixed_host(self._ctx, kinds.ctypes.data, msg32.ctypes.data, key64.ctypes.data,
                                                   sig64.ctypes.data, n, out.ctypes.data), "sv_verify_mixed_host")
         return out[:n]
+
+    def verify_schnorr_batch(self, msg32, xonly32, sig64, seed32=None):
+        """BIP-340 batch verification (random linear combination per group of 1024, one-by-one for failed groups).
+        Returns (verdicts, groups_total, groups_failed)."""
+        msg32, xonly32, sig64 = _u8(msg32, 32), _u8(xonly32, 32), _u8(sig64, 64)
+        n = msg32.shape[0]
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        gt, gf = ctypes.c_uint32(), ctypes.c_uint32()
+        seed = np.ascontiguousarray(np.frombuffer(bytes(seed32), dtype=np.uint8)) if seed32 is not None else None
+        self._check(self.lib.sv_verify_schnorr_batch_host(self._ctx, msg32.ctypes.data, xonly32.ctypes.data, sig64.ctypes.data, n,
+                                                          seed.ctypes.data if seed is not None else None, out.ctypes.data,
+                                                          ctypes.byref(gt), ctypes.byref(gf)), "sv_verify_schnorr_batch_host")
+        return out[:n], gt.value, gf.value
 
     def set_dedup(self, on=True):
         self._check(self.lib.sv_set_dedup(self._ctx, 1 if on else 0), "sv_set_dedup")

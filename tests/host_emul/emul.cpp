@@ -13,6 +13,7 @@
 #include <vector>
 #include "../../lightning_b200/csrc/verify.cuh"
 #include "../../lightning_b200/csrc/selftest.cuh"
+#include "../../lightning_b200/csrc/batch.cuh"
 
 static std::vector<ge_mem> g_table;
 static std::vector<ge_mem> g_bases(16);
@@ -187,6 +188,28 @@ void emul_verify_small_batch(int kind, const u8* msg, const u8* key, const u8* s
     sv_small_item it;
     for (size_t i = 0; i < n; i++)
         out[i] = (u8)verify_small_sequential(kind, msg + 32 * i, key + keylen * i, sig + 64 * i, g_table.data(), &it);
+}
+
+// BIP-340 batch verification (batch.cuh), every stage on the host with the straightforward window sum: ok[i] = encoding
+// check, group_ok[g] = the group's equation held
+void emul_schnorr_batch(const u8* msg, const u8* xonly, const u8* sig, size_t n, const u8* seed32, u8* ok, u8* group_ok) {
+    build_gtable_fast();
+    std::vector<qtab_entry> pts(2 * n);
+    std::vector<signed char> dig((size_t)SV_SB_WINDOWS * 4 * n);
+    std::vector<sc> t(n);
+    for (size_t i = 0; i < n; i++)
+        ok[i] = sb_prepare(msg + 32 * i, xonly + 32 * i, sig + 64 * i, seed32, i, &pts[2 * i], &dig[4 * i], 4 * n, t[i]) ? 1 : 0;
+    size_t groups = (n + SV_SB_GROUP - 1) / SV_SB_GROUP;
+    for (size_t g = 0; g < groups; g++) {
+        size_t first = g * SV_SB_GROUP, members = (n - first < SV_SB_GROUP) ? (n - first) : SV_SB_GROUP;
+        sv_jac S[SV_SB_WINDOWS];
+        for (int w = 0; w < SV_SB_WINDOWS; w++) {
+            gej W;
+            sb_window_sum_reference(W, &pts[2 * first], &dig[(size_t)w * 4 * n + 4 * first], (u32)(members * SV_SB_TERMS));
+            small_jac_store(&S[w], W);
+        }
+        group_ok[g] = sb_group_check(S, &t[first], (u32)members, g_table.data()) ? 1 : 0;
+    }
 }
 
 // full verification of a batch, same data flow as the kernels (prep in groups of SV_PREP_BATCH)

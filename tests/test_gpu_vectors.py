@@ -358,3 +358,42 @@ def test_gossip_key_deduplication_same_status(engine, cln):
             want = cln.cln_sigcheck_channel_update(m, L_, P(np.ascontiguousarray(signers[i])))
         assert a[i] == want, (i, a[i], want)
     assert (a == 0).sum() > 0.8 * len(batch) and (a != 0).sum() > 100
+
+
+def test_bip340_batch_verification_rlc(engine, ref):
+    """Row N3: BIP-340 batch verification by random linear combination on the device.  Every verdict equals the reference's
+    per-signature verdict: all-valid batches (every group passes), sparse bad signatures (only their groups fall back to
+    one-by-one verification), the 10 %-corrupted mix (every group falls back), encoding failures (excluded, no fallback
+    needed), ragged sizes, different seeds and the system's own randomness."""
+    n = 5000
+    w = util.make_signed(ref, n, seed=88)
+    msg, key, sig = w["msg"], w["xonly"], w["ssig"]
+    v, gt, gf = engine.verify_schnorr_batch(msg, key, sig, seed32=bytes(range(32)))
+    assert v.all() and gt == 5 and gf == 0
+    v, gt, gf = engine.verify_schnorr_batch(msg, key, sig)  # seed from getrandom()
+    assert v.all() and gf == 0
+    for m in (1, 2, 31, 1023, 1024, 1025, 2049):
+        v, gt, gf = engine.verify_schnorr_batch(msg[:m], key[:m], sig[:m], seed32=bytes(32))
+        assert v.all() and gt == (m + 1023) // 1024 and gf == 0, m
+    # sparse damage: three bad signatures in two groups, two encoding failures elsewhere
+    m2, k2, s2 = msg.copy(), key.copy(), sig.copy()
+    m2[100, 0] ^= 1
+    s2[200, 45] ^= 4
+    k2[3000] = k2[3001]
+    s2[4500, :32] = 255
+    k2[4600, :] = 0
+    k2[4600, 31] = 5
+    want = util.ref_verify(ref, 2, m2, k2, s2, threads=4)
+    v, gt, gf = engine.verify_schnorr_batch(m2, k2, s2, seed32=bytes(range(32)))
+    assert np.array_equal(v, want) and list(np.nonzero(want == 0)[0]) == [100, 200, 3000, 4500, 4600]
+    assert gf == 2  # groups 0 and 2; the encoding failures in group 4 needed no fallback
+    # heavy damage: every group falls back, verdicts still exact
+    w3 = util.corrupt(util.make_signed(ref, 4000, seed=89), every=10)
+    want = util.ref_verify(ref, 2, w3["msg"], w3["xonly"], w3["ssig"], threads=4)
+    v, gt, gf = engine.verify_schnorr_batch(w3["msg"], w3["xonly"], w3["ssig"], seed32=bytes(32))
+    assert np.array_equal(v, want) and gf == gt == 4 and 0 < want.sum() < want.size
+    # BIP-340's own vectors (valid and invalid ones in one batch)
+    vec = json.load(open(os.path.join(GOLD, "bip340.json")))
+    m, k, s = (np.concatenate([H(x[f], z) for x in vec]) for f, z in (("msg32", 32), ("xonly", 32), ("sig64", 64)))
+    v, _, _ = engine.verify_schnorr_batch(m, k, s, seed32=bytes(32))
+    assert list(v) == [x["expected"] for x in vec]

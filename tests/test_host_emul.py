@@ -362,3 +362,44 @@ def test_small_batch_path_all_vector_sets(emul, ref):
         assert small(2, h(v["msg32"], 32), h(v["xonly"], 32), h(v["sig64"], 64))[0] == v["expected"], v["index"]
     for c in json.load(open(os.path.join(GOLD, "ecdsa_edge_cases.json"))):
         assert small(0, h(c["msg32"], 32), h(c["pub33"], 33), h(c["sig64"], 64))[0] == c["expected"], c["name"]
+
+
+def test_bip340_batch_verification_group_equations(emul, ref):
+    """Row N3: random-linear-combination batch verification, host build of every stage (preparation, signed 6-bit recoding,
+    bucket window sums, Horner combination, G term): a group of valid signatures satisfies its equation whatever the seed;
+    one bad signature (wrong message, flipped s, someone else's key) fails ITS group only; encoding failures (r >= p, s >= n,
+    x not on the curve) are excluded and do not poison the group."""
+    n = 1024 + 90  # one full group and a ragged one
+    w = util.make_signed(ref, n, seed=77)
+    msg, key, sig = w["msg"].copy(), w["xonly"].copy(), w["ssig"].copy()
+    want = util.ref_verify(ref, 2, msg, key, sig, threads=4)
+    assert want.all()
+
+    def run(m, k, s, seed):
+        ok = np.zeros(n, np.uint8)
+        gok = np.zeros(2, np.uint8)
+        sd = np.frombuffer(seed, dtype=np.uint8).copy()
+        emul.emul_schnorr_batch(P(np.ascontiguousarray(m)), P(np.ascontiguousarray(k)), P(np.ascontiguousarray(s)), ctypes.c_size_t(n), P(sd), P(ok), P(gok))
+        return ok, gok
+    for seed in (bytes(32), bytes(range(32))):
+        ok, gok = run(msg, key, sig, seed)
+        assert ok.all() and list(gok) == [1, 1]
+    # encoding failures drop out without poisoning
+    s2, k2 = sig.copy(), key.copy()
+    s2[5, :32] = 255        # r >= p
+    s2[6, 32:] = 255        # s >= n
+    k2[7, :] = 0
+    k2[7, 31] = 5           # x = 5 is not on the curve
+    ok, gok = run(msg, k2, s2, bytes(range(32)))
+    assert list(np.nonzero(ok == 0)[0]) == [5, 6, 7] and list(gok) == [1, 1]
+    assert not util.ref_verify(ref, 2, msg[5:8], k2[5:8], s2[5:8]).any()
+    # a well-formed but wrong signature fails its own group only
+    for mutate, grp in ((lambda m, k, s: m.__setitem__((1050, 3), m[1050, 3] ^ 1), 1), (lambda m, k, s: s.__setitem__((17, 40), s[17, 40] ^ 2), 0),
+                        (lambda m, k, s: k.__setitem__(300, k[301].copy()), 0)):
+        m3, k3, s3 = msg.copy(), key.copy(), sig.copy()
+        mutate(m3, k3, s3)
+        ok, gok = run(m3, k3, s3, bytes(range(32)))
+        if ok.all():  # (a flipped s may land >= n: then it is an encoding failure instead)
+            expect = [1, 1]
+            expect[grp] = 0
+            assert list(gok) == expect
