@@ -78,7 +78,7 @@ def build_host_emul(force=False):
     srcs = _sources(CSRC, (".cuh",)) + [src]
     if not force and _newer(EMUL, srcs):
         return EMUL
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unused-function", "-o", EMUL, src]
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wall", "-Wno-unused-function", "-o", EMUL, src]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ (host_emul) failed:\n" + r.stdout + r.stderr)

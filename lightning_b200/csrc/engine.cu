@@ -184,12 +184,11 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     }
 }
 
-// ---- small-batch path (verify.cuh "small-batch path"): one CTA = 3 warps x up to 32 items, lane l of every warp works
-// on item l.  The inputs may live in host-mapped pinned memory (zero-copy: the CTA pulls its items into shared memory
+// ---- small-batch path (verify.cuh "small-batch path"): one CTA = 5 warps x up to 32 items.  The inputs may live in host-mapped pinned memory (zero-copy: the CTA pulls its items into shared memory
 // with warp-coalesced loads) or in device memory.  aux (optional): bit 0 = key decoded, bit 1 = signature encoding parsed.
 #define SV_SMALL_ITEMS 32
 template <int KIND>
-__global__ void __launch_bounds__(96, 1)
+__global__ void __launch_bounds__(160, 1)
     k_small(const u8* __restrict__ msg, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
             const ge_mem* __restrict__ gtab, u8* __restrict__ verdict, u8* __restrict__ aux) {
     constexpr int keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
@@ -204,8 +203,9 @@ __global__ void __launch_bounds__(96, 1)
     for (int t = threadIdx.x; t < cnt * 64; t += blockDim.x) in_sig[t] = sig[64 * base + t];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // phase A (warps 0, 1) and the comb / finish: lane l works on item l; idle lanes redo item 0 into their own slot
     const bool active = lane < cnt;
-    const int j = active ? lane : 0;  // idle lanes redo item 0 into their own slot and discard it
+    const int j = active ? lane : 0;
     sv_small_item* it = &items[lane];
     const u8* m = in_msg + 32 * j;
     const u8* k = in_key + keylen * j;
@@ -213,9 +213,14 @@ __global__ void __launch_bounds__(96, 1)
     if (warp == 0) small_key_side(KIND, k, it);
     else if (warp == 1) small_scalar_side(KIND, m, k, sg, it);
     __syncthreads();
-    if (warp == 0) small_half_ladder(it, 0);
-    else if (warp == 1) small_half_ladder(it, 1);
-    else small_comb(it, gtab);
+    // phase B: warps 0..3 run the half ladders on lane PAIRS (warp w: half w >> 1, items 16 (w & 1) + lane / 2), warp 4 the comb
+    if (warp < 4) {
+        pair_lane L;
+        L.role = lane & 1;
+        small_half_ladder_pair(L, &items[16 * (warp & 1) + (lane >> 1)], warp >> 1);
+    } else {
+        small_comb(it, gtab);
+    }
     __syncthreads();
     if (warp == 0) {
         bool kd;
@@ -1203,9 +1208,9 @@ static int launch_small(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key,
     unsigned grid = (unsigned)((n + SV_SMALL_ITEMS - 1) / SV_SMALL_ITEMS);
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
-    if (kind == SV_KIND_ECDSA33) k_small<SV_KIND_ECDSA33><<<grid, 96, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
-    else if (kind == SV_KIND_ECDSA_XY) k_small<SV_KIND_ECDSA_XY><<<grid, 96, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
-    else k_small<SV_KIND_SCHNORR><<<grid, 96, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    if (kind == SV_KIND_ECDSA33) k_small<SV_KIND_ECDSA33><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else if (kind == SV_KIND_ECDSA_XY) k_small<SV_KIND_ECDSA_XY><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else k_small<SV_KIND_SCHNORR><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
     ctx->launches += 1;
     CK(cudaGetLastError());

@@ -637,6 +637,156 @@ SV_HD u32 small_finish(int kind, sv_small_item* it, const u8* sig64, bool* key_o
     u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64, true) : ecdsa_final(R, sig64, flags);
     return ok ? v : 0u;
 }
+// ---- half ladder on a PAIR of lanes -------------------------------------------------------------------------------
+// A half ladder is one dependent chain of 128 doublings and 33 additions: 1,259 field multiplications one after another
+// set the latency of a lone verification.  Inside one doubling / addition, however, several multiplications are independent
+// of each other; two neighbouring lanes (2k, 2k+1) of a warp therefore share one half ladder: each step both lanes multiply
+// (different operands), results they need from each other cross with warp shuffles.  A doubling takes 4 multiplication
+// steps instead of 7, a mixed addition 6 instead of 11.  Both lanes hold the full point before and after every operation.
+// The case analysis is that of gej_double / gej_add_ge.
+struct pair_lane {
+    int role;  // 0 / 1 inside the pair
+#if !SV_DEVICE_CODE
+    struct pair_mailbox* mb;  // host build: the two lanes are two threads meeting at a mailbox (tests/host_emul)
+#endif
+};
+#if SV_DEVICE_CODE
+SV_HD void pair_swap(const pair_lane&, fe& recv, const fe& send) {
+    unsigned m = __activemask();  // both lanes of a pair always take the same branches
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) recv.v[i] = __shfl_xor_sync(m, send.v[i], 1);
+}
+#else
+SV_HD void pair_swap(const pair_lane& L, fe& recv, const fe& send);  // tests/host_emul/emul.cpp
+#endif
+SV_HD void fe_sel(fe& r, bool c, const fe& a, const fe& b) {  // r = c ? a : b
+    SV_UNROLL
+    for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
+}
+
+// R = 2R.  steps: [A = X^2 | B = Y^2]  [T = Y*Z | C = B^2]  [S = (X+B)^2 | EE = (3A)^2]  [ - | M = E*(D - X3)]
+SV_HD void pair_double(const pair_lane& L, gej& R) {
+    const bool r1 = L.role != 0;
+    fe a, b, t, u, o1, o2;
+    fe_sel(t, r1, R.y, R.x);
+    fe_sqr(a, t);                       // lane0: A          lane1: B
+    fe_sel(o1, r1, a, R.y);
+    fe_sel(o2, r1, a, R.z);
+    fe_mul(b, o1, o2);                  // lane0: T = Y*Z    lane1: C = B^2
+    pair_swap(L, t, a);                 // lane0 gets B      lane1 gets A
+    fe e;
+    fe_mul3(e, r1 ? t : a);             // E = 3A (meaningful on lane 1; lane 0 computes it too: it holds A in `a`)
+    fe_add(u, R.x, r1 ? a : t);         // X + B
+    fe_sel(o1, r1, e, u);
+    fe s;
+    fe_sqr(s, o1);                      // lane0: S = (X+B)^2   lane1: EE = E^2
+    fe A_, C_;
+    fe_sel(A_, r1, t, a);               // A on both lanes
+    pair_swap(L, u, r1 ? b : s);        // lane0 sends S, lane1 sends C:  lane0 gets C, lane1 gets S
+    fe S_;
+    fe_sel(S_, r1, u, s);
+    fe_sel(C_, r1, b, u);
+    fe d;
+    fe_sub(d, S_, A_);
+    fe_sub(d, d, C_);
+    fe_dbl(d, d);                       // D on both lanes
+    fe x3, m, c8, z3;
+    fe_sub(x3, s, d);                   // lane1: X3 = EE - 2D (lane 0: garbage)
+    fe_sub(x3, x3, d);
+    fe_sub(t, d, x3);
+    fe_mul(m, e, t);                    // lane1: M = E*(D - X3)
+    fe_mul8(c8, C_);
+    fe y3;
+    fe_sub(y3, m, c8);                  // lane1: Y3
+    fe_dbl(z3, b);                      // lane0: Z3 = 2T
+    pair_swap(L, t, r1 ? x3 : z3);      // lane0 gets X3, lane1 gets Z3
+    pair_swap(L, u, y3);                // lane0 gets Y3
+    fe_sel(R.x, r1, x3, t);
+    fe_sel(R.y, r1, y3, u);
+    fe_sel(R.z, r1, t, z3);
+}
+
+// R = R + p (p affine).  steps: [zz = Z^2 | -] [u2 = px*zz | zzz = Z*zz] [hh = h^2 | s2 = py*zzz] [hhh = h*hh | rr^2]
+//                              [v = X*hh | Z3 = Z*h] [rr*(v - X3) | hhh*Y]
+SV_HD void pair_add_ge(const pair_lane& L, gej& R, const ge& p) {
+    const bool r1 = L.role != 0;
+    if (R.inf) {
+        gej_set_ge(R, p);
+        return;
+    }
+    fe zz, t, u, w, h, rr, o1, o2;
+    fe_sqr(zz, R.z);                    // both lanes (same operand): zz
+    fe_sel(o1, r1, R.z, p.x);
+    fe_mul(t, o1, zz);                  // lane0: u2 = px*zz     lane1: zzz = Z*zz
+    fe_sub(h, t, R.x);                  // lane0: h
+    fe_sel(o1, r1, p.y, h);
+    fe_sel(o2, r1, t, h);
+    fe_mul(u, o1, o2);                  // lane0: hh = h^2       lane1: s2 = py*zzz
+    fe_sub(rr, u, R.y);                 // lane1: rr
+    pair_swap(L, w, r1 ? rr : h);       // lane0 gets rr, lane1 gets h
+    fe H_, RR_;
+    fe_sel(H_, r1, w, h);
+    fe_sel(RR_, r1, rr, w);
+    if (fe_is_zero(H_)) {               // same x: double or cancel (group_impl.h:595-605); both lanes agree on the branch
+        if (fe_is_zero(RR_)) pair_double(L, R);
+        else {
+            R.inf = 1;
+            fe_set_zero(R.x); fe_set_zero(R.y); fe_set_zero(R.z);
+        }
+        return;
+    }
+    fe_sel(o1, r1, RR_, H_);
+    fe_sel(o2, r1, RR_, u);
+    fe q;
+    fe_mul(q, o1, o2);                  // lane0: hhh = h*hh     lane1: rr2 = rr^2
+    fe_sel(o1, r1, R.z, R.x);
+    fe_sel(o2, r1, H_, u);
+    fe g;
+    fe_mul(g, o1, o2);                  // lane0: v = X*hh       lane1: Z3 = Z*h
+    pair_swap(L, w, q);                 // lane0 gets rr2, lane1 gets hhh
+    fe x3;
+    fe_sub(x3, w, q);                   // lane0: rr2 - hhh
+    fe_sub(x3, x3, g);
+    fe_sub(x3, x3, g);                  // lane0: X3 = rr2 - hhh - 2v
+    fe_sub(t, g, x3);                   // lane0: v - X3
+    fe_sel(o1, r1, w, RR_);
+    fe_sel(o2, r1, R.y, t);
+    fe m;
+    fe_mul(m, o1, o2);                  // lane0: rr*(v - X3)    lane1: hhh*Y
+    pair_swap(L, t, m);                 // lane0 gets hhh*Y
+    fe y3;
+    fe_sub(y3, m, t);                   // lane0: Y3
+    pair_swap(L, w, r1 ? g : x3);       // lane0 gets Z3, lane1 gets X3
+    pair_swap(L, u, y3);                // lane1 gets Y3
+    fe_sel(R.x, r1, w, x3);
+    fe_sel(R.y, r1, u, y3);
+    fe_sel(R.z, r1, g, w);
+    R.inf = 0;
+}
+SV_HD void ecmult_half_ladder_pair(const pair_lane& L, gej& R, const u32* mag, bool lam, const qtab_entry* tab) {
+    u32 t = mag[4];
+    u32 sgn = t >> 31;
+    ge p;
+    qtable_fetch(p, tab, ((t >> 1) & 7u) + 8u, sgn, lam);
+    gej_set_ge(R, p);
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+    for (int i = 31; i >= 0; i--) {
+#if SV_DEVICE_CODE
+#pragma unroll 1
+#endif
+        for (int j = 0; j < 4; j++) pair_double(L, R);
+        qtable_fetch(p, tab, window4(mag, i), sgn, lam);
+        pair_add_ge(L, R, p);
+    }
+}
+SV_HD void small_half_ladder_pair(const pair_lane& L, sv_small_item* it, int half) {
+    gej R;
+    ecmult_half_ladder_pair(L, R, half ? it->w.k2 : it->w.k1, half != 0, it->tab);
+    if (L.role == 0) small_jac_store(half ? &it->r2 : &it->r1, R);
+}
+
 // the three phases run one after another (host build of the kernel source, tests/host_emul)
 SV_HD u32 verify_small_sequential(int kind, const u8* msg32, const u8* key, const u8* sig64, const ge_mem* gtab,
                                   sv_small_item* it) {

@@ -7,11 +7,33 @@
 // construction, accept/reject rules, SHA-256) can be differential-tested against the oracle on a
 // machine without a GPU.  It is NOT part of the product: libcln_sigverify.so never contains or
 // calls this code, and the engine has no CPU execution path.
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include "../../lightning_b200/csrc/common.cuh"
+struct fe;
+// host stand-in for the warp shuffle between the two lanes of a pair (verify.cuh pair_swap): the lanes are two threads
+// that meet at a mailbox; a sense-reversing barrier on atomics orders the exchange
+struct pair_mailbox {
+    std::atomic<int> arrived{0};
+    std::atomic<int> gen{0};
+    unsigned slot[2][8];
+    void barrier() {
+        int g = gen.load();
+        if (arrived.fetch_add(1) == 1) { arrived.store(0); gen.fetch_add(1); }
+        else while (gen.load() == g) std::this_thread::yield();
+    }
+};
 #include "../../lightning_b200/csrc/verify.cuh"
+static inline void pair_swap(const pair_lane& L, fe& recv, const fe& send) {
+    memcpy(L.mb->slot[L.role], send.v, 32);
+    L.mb->barrier();
+    memcpy(recv.v, L.mb->slot[1 - L.role], 32);
+    L.mb->barrier();
+}
 #include "../../lightning_b200/csrc/selftest.cuh"
 #include "../../lightning_b200/csrc/batch.cuh"
 
@@ -209,6 +231,28 @@ void emul_schnorr_batch(const u8* msg, const u8* xonly, const u8* sig, size_t n,
             small_jac_store(&S[w], W);
         }
         group_ok[g] = sb_group_check(S, &t[first], (u32)members, g_table.data()) ? 1 : 0;
+    }
+}
+
+// the small-batch path with the half ladders on lane PAIRS (two host threads per half ladder), as k_small runs it
+void emul_verify_small_pair_batch(int kind, const u8* msg, const u8* key, const u8* sig, size_t n, u8* out) {
+    build_gtable_fast();
+    size_t keylen = kind == SV_KIND_ECDSA33 ? 33 : (kind == SV_KIND_ECDSA_XY ? 64 : 32);
+    sv_small_item it;
+    for (size_t i = 0; i < n; i++) {
+        small_key_side(kind, key + keylen * i, &it);
+        small_scalar_side(kind, msg + 32 * i, key + keylen * i, sig + 64 * i, &it);
+        for (int half = 0; half < 2; half++) {
+            pair_mailbox mb;
+            std::thread other([&] { pair_lane L; L.role = 1; L.mb = &mb; small_half_ladder_pair(L, &it, half); });
+            pair_lane L;
+            L.role = 0;
+            L.mb = &mb;
+            small_half_ladder_pair(L, &it, half);
+            other.join();
+        }
+        small_comb(&it, g_table.data());
+        out[i] = (u8)small_finish(kind, &it, sig + 64 * i);
     }
 }
 
