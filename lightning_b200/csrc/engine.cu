@@ -45,6 +45,11 @@
 #ifndef SV_MAIN_MINB
 #define SV_MAIN_MINB (512 / SV_MAIN_BLOCK)
 #endif
+#ifdef SV_COMB_SMEM
+#define SV_MAIN_SMEM (17 * 128 * 64)  // the variant's shared-memory comb table
+#else
+#define SV_MAIN_SMEM 0
+#endif
 
 // -------------------------------------------------------------------------------------------------
 // kernels
@@ -128,11 +133,44 @@ __global__ void __launch_bounds__(128) k_prep_schnorr(const u8* msg, const u8* k
 // (They must not alias a live record: the BIP-340 path overwrites records with the parked R.)
 __device__ sv_work g_idle_work = {{1, 0, 0, 0, 0}, {1, 0, 0, 0, 0}, {0}, 0, {0}};
 
+#ifdef SV_COMB_SMEM
+__device__ const ge_mem* g_t8;  // 17 x 128 entries d * 2^(8 i) * G in global memory, source of the per-CTA shared copy
+__global__ void k_t8_fill(ge_mem* t8, const ge_mem* gtab) {
+    u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 17 * 128) return;
+    u32 row = e / 128, d = e % 128 + 1;  // d * 2^(8 row) G = (d << (8 (row & 1))) * 2^(16 (row / 2)) G
+    t8[e] = gtab[(size_t)(row >> 1) * SV_GT_ROW + ((d << (8 * (row & 1))) - 1)];
+}
+#endif
 template <int KIND>
 __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main(sv_work* work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
            const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict, u8* keyok) {
     const size_t keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
+#ifdef SV_COMB_SMEM
+    // VARIANT: the 17 x 128-entry 8-bit comb (136 KiB) is staged in shared memory once per (persistent) CTA by ONE bulk
+    // asynchronous copy (cp.async.bulk: the TMA engine, UBLKCP in SASS), completion signalled on an mbarrier
+    {
+        extern __shared__ __align__(16) unsigned char sv_smem_raw[];
+        __shared__ __align__(8) unsigned long long sv_bar;
+        const unsigned bytes = 17u * 128u * (unsigned)sizeof(ge_mem);
+        unsigned bar = (unsigned)__cvta_generic_to_shared(&sv_bar), dst = (unsigned)__cvta_generic_to_shared(sv_smem_raw);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(g_t8), "r"(bytes), "r"(bar) : "memory");
+        }
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+#endif
 #ifndef SV_MAP_INTERLEAVED
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -1051,7 +1089,7 @@ extern "C" int sv_create(sv_ctx** out, int device) {
         CK2(cudaMalloc(&ctx->d_sink, 64));
         CK2(cudaHostAlloc((void**)&ctx->h_small, (size_t)SV_SMALL_CAP * (32 + 64 + 64 + 2), cudaHostAllocMapped | cudaHostAllocPortable));
         int occ = 0;
-        CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_main<SV_KIND_ECDSA33>, SV_MAIN_BLOCK, 0));
+        CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_main<SV_KIND_ECDSA33>, SV_MAIN_BLOCK, SV_MAIN_SMEM));
         if (occ < 1) occ = 1;
         ctx->main_grid = ctx->sm_count * occ;
         ctx->scratch_bytes = (size_t)ctx->main_grid * SV_MAIN_BLOCK * 8 * sizeof(qtab_entry);
@@ -1075,6 +1113,18 @@ extern "C" int sv_create(sv_ctx** out, int device) {
         k_gtable_fill<<<(SV_GT_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_gtab, ctx->d_bases);
         ctx->launches += 2;
         CK2(cudaGetLastError());
+#ifdef SV_COMB_SMEM
+        {
+            ge_mem* t8 = nullptr;
+            CK2(cudaMalloc(&t8, 17 * 128 * sizeof(ge_mem)));
+            k_t8_fill<<<17, 128, 0, ctx->stream>>>(t8, ctx->d_gtab);
+            CK2(cudaMemcpyToSymbolAsync(g_t8, &t8, sizeof(t8), 0, cudaMemcpyHostToDevice, ctx->stream));
+            const int smem = 17 * 128 * (int)sizeof(ge_mem);
+            CK2(cudaFuncSetAttribute(k_main<SV_KIND_ECDSA33>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CK2(cudaFuncSetAttribute(k_main<SV_KIND_ECDSA_XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CK2(cudaFuncSetAttribute(k_main<SV_KIND_SCHNORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        }
+#endif
         CK2(cudaStreamSynchronize(ctx->stream));
 #undef CK2
     } while (0);
@@ -1248,12 +1298,12 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
     if (kind == SV_KIND_ECDSA33)
-        k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
+        k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
     else if (kind == SV_KIND_ECDSA_XY)
-        k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
+        k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
     else
     {
-        k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
+        k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
         size_t threads = (n + SV_FINAL_BATCH - 1) / SV_FINAL_BATCH;
         k_final_schnorr<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(work, d_sig, n, d_verdict);
         ctx->launches += 1;

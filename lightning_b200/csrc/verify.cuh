@@ -122,15 +122,19 @@ SV_HD void ecdsa_finish_prep(sv_work& w, bool ok, const sc& r, const sc& m, cons
     sc u1, u2;
     sc_mul(u1, sinv, m);
     sc_mul(u2, sinv, r);
+    SV_UNROLL
+    for (int i = 0; i < 5; i++) w.pad[i] = 0;
     sc_prepare_u2(w, u2);
+#ifdef SV_COMB_SMEM
+    sc_prepare_u1_smem(w, u1);
+#else
     sc_prepare_u1(w, u1);
+#endif
     // second x candidate r + n exists iff r < p - n (ecdsa_impl.h:253-259; constant :32-34)
     const u32 pmn[8] = {0x2FC9BAEEu, 0x402DA172u, 0x50B75FC4u, 0x45512319u, 0x00000001u, 0, 0, 0};
     u32 t[8];
     u32 bw = u256_sub(t, r.v, pmn);
     w.flags = SV_WF_VALID | SV_WF_PARSED | (bw ? SV_WF_R_PLUS_N : 0u);
-    SV_UNROLL
-    for (int i = 0; i < 5; i++) w.pad[i] = 0;
 }
 
 // BIP-340: R = s*G + (-e)*P with e = H_tag(r || P.x || m) mod n.   Rejects r >= p
@@ -150,11 +154,15 @@ SV_HD void schnorr_prep(sv_work& w, const u8* sig64, const u8* xonly32, const u8
     sha256_bip340_challenge(h, sig64, xonly32, msg32);
     sc_set_b32(e, h, nullptr);
     sc_negate(ne, e);
-    sc_prepare_u2(w, ne);
-    sc_prepare_u1(w, s);
-    w.flags = SV_WF_VALID;
     SV_UNROLL
     for (int i = 0; i < 5; i++) w.pad[i] = 0;
+    sc_prepare_u2(w, ne);
+#ifdef SV_COMB_SMEM
+    sc_prepare_u1_smem(w, s);
+#else
+    sc_prepare_u1(w, s);
+#endif
+    w.flags = SV_WF_VALID;
 }
 
 // Montgomery's trick: invert n (<= SV_PREP_BATCH) non-zero scalars with ONE exponentiation.
@@ -337,6 +345,36 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
     // leave the scaled curve: true Z = Z * zc
     fe_mul(R.z, R.z, zc);
     // fixed-base comb
+#if defined(SV_COMB_SMEM) && SV_DEVICE_CODE
+    // VARIANT: 8-bit GLV comb against the 131 KB table staged in shared memory (k_main copies it in with one bulk copy):
+    // 2 x 17 windows -> up to 34 mixed additions and a beta multiplication for each lambda-half point
+    {
+        extern __shared__ __align__(16) unsigned char sv_smem_raw[];
+        const ge_mem* t8 = reinterpret_cast<const ge_mem*>(sv_smem_raw);
+        fe beta;
+        SV_UNROLL
+        for (int i = 0; i < 8; i++) beta.v[i] = GE_BETA[i];
+        const u32 top = w->pad[0];
+#pragma unroll 1
+        for (int row = 0; row < 17; row++) {
+            SV_SYNC(sync_threads);
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                int d;
+                if (row < 16) d = half ? (int)(short)((u32)w->gd[row] >> 16) : (int)(short)((u32)w->gd[row] & 0xFFFFu);
+                else d = (int)(signed char)((top >> (8 * half)) & 0xFFu);
+                u32 sneg = (top >> (16 + half)) & 1u;
+                if (d != 0) {
+                    u32 a = (u32)(d < 0 ? -d : d);
+                    ge_from_mem(p, t8 + (size_t)row * 128 + (a - 1));
+                    if (half) fe_mul(p.x, p.x, beta);
+                    if ((d < 0) != (sneg != 0)) fe_neg(p.y, p.y);
+                    gej_add_ge(R, R, p);
+                }
+            }
+        }
+    }
+#else
 #if SV_DEVICE_CODE
 #pragma unroll 1
 #endif
@@ -350,6 +388,7 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
             gej_add_ge(R, R, p);
         }
     }
+#endif
 }
 
 SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* gtab, qtab_entry* tab,

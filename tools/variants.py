@@ -19,6 +19,8 @@ VARIANTS = {
     "alu_folds": ["-DSV_ALU_FOLDS"],
     "reduce_noacc": ["-DSV_REDUCE_NOACC"],
     "alu_folds+noacc": ["-DSV_ALU_FOLDS", "-DSV_REDUCE_NOACC"],
+    # the 8-bit GLV comb staged in shared memory by one bulk (TMA) copy: 1 CTA of 512 threads per SM (136 KiB of shared memory)
+    "comb_smem": ["-DSV_COMB_SMEM", "-DSV_MAIN_BLOCK=512", "-DSV_MAIN_MINB=1"],
     "sync_w1": ["-USV_SYNC_WINDOWS", "-DSV_SYNC_WINDOWS=1"],
     "sync_w4": ["-USV_SYNC_WINDOWS", "-DSV_SYNC_WINDOWS=4"],
 }
