@@ -57,8 +57,18 @@ def build_engine(force=False, verbose=False, extra_flags=()):
                         "-o", dropin_o], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("gcc (cln_dropin.c) failed:\n" + r.stdout + r.stderr)
+    # the batch-verification kernels are a translation unit of their own, compiled with the field multiplier as real
+    # functions (see batch.cu); everything else inlines it
+    batch_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-DSV_FE_INLINE", "-DSV_MAIN_SYNC")] + ["-DSV_NO_SYNC_INLINE", "-c"]
+    batch_o = os.path.join(CSRC, "batch.o")
+    r = subprocess.run([nvcc] + batch_flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", batch_o, os.path.join(CSRC, "batch.cu")],
+                       capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc (batch.cu) failed:\n" + r.stdout + r.stderr)
     cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB, os.path.join(CSRC, "engine.cu"), dropin_o]
+        "-o", LIB, os.path.join(CSRC, "engine.cu"), batch_o, dropin_o]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

@@ -36,7 +36,7 @@ def build():
         os.makedirs(d, exist_ok=True)
         base = [f for f in b.NVCC_FLAGS if not (name.startswith("sync_w") and f.startswith("-DSV_SYNC_WINDOWS"))]
         cmd = [nvcc] + base + [f for f in flags if not f.startswith("-U")] + ["-o", os.path.join(d, "libcln_sigverify.so"),
-                                                                             os.path.join(b.CSRC, "engine.cu"), dropin_o]
+                                                                             os.path.join(b.CSRC, "engine.cu"), os.path.join(b.CSRC, "batch.o"), dropin_o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         print(name, "ok" if r.returncode == 0 else "FAILED\n" + r.stderr[-2000:])
 
