@@ -248,6 +248,7 @@ typedef struct {
     size_t gtable_bytes;
     size_t scratch_bytes;
     unsigned long long launches; /* kernels launched by this context so far */
+    size_t l2_persist_bytes;     /* persisting L2 carve-out behind the table-slab access-policy window (0: hint off) */
 } sv_info;
 int sv_get_info(const sv_ctx *ctx, sv_info *info);
 
