@@ -504,7 +504,7 @@ def run_engine(args):
         "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32 carry chains)", "data": data_note,
         "config": bench_config(world),
         "engine": {"main_grid": info["main_grid"], "main_block": info["main_block"], "main_regs": info["main_regs"],
-                   "launch_streams": 1 if streams[1] is streams[0] else 2, "l2_persist_bytes": info.get("l2_persist_bytes")},
+                   "launch_streams": 1 if streams[1] is streams[0] else 2, "l2_persist_bytes": info.get("l2_persist_bytes"), "l2_max_persist_bytes": info.get("l2_max_persist_bytes")},
         "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": n * 129, "d2h_bytes_per_step": n,
                 "steps": e2e_steps, "seconds": float(t_e.item()), "verdicts_as_constructed": e2e_matches},
         "sustained": sustained,

@@ -249,6 +249,7 @@ typedef struct {
     size_t scratch_bytes;
     unsigned long long launches; /* kernels launched by this context so far */
     size_t l2_persist_bytes;     /* persisting L2 carve-out behind the table-slab access-policy window (0: hint off) */
+    size_t l2_max_persist_bytes; /* what the device would allow */
 } sv_info;
 int sv_get_info(const sv_ctx *ctx, sv_info *info);
 

@@ -434,11 +434,13 @@ SV_HD void fe_reduce512(fe& r, const u32 t[16]) {
 
 // reference: secp256k1_fe_mul (field_5x52_int128_impl.h:18), secp256k1_fe_sqr (:154)
 //
-// On the device these two are REAL FUNCTIONS (operands and result by value: the sm_100a ABI keeps all
-// 24 words in registers, no stack traffic).  ncu on the fully-inlined kernel showed the warps starved
-// for instructions (stall_no_instruction 4.5 per issue, issue slots 39 % busy): the ladder body was
-// ~44 KB of straight-line code against a 32 KB L1.5 / ~6 KB L0 instruction cache.  As functions the two
-// bodies (~4 KB together) stay L0-resident and carry ~85 % of all executed instructions.
+// Two device forms, chosen per translation unit:
+//   -DSV_FE_INLINE (engine.cu, every kernel but the batch ones): inlined.  The curve kernel keeps the warps of a CTA at the
+//     same program counter with CTA-wide barriers so that they share instruction fetches of the large straight-line code
+//     (46 M verifies/s; without the barriers the inlined ladder starves on instruction fetch, 25.9 M/s).
+//   otherwise (batch.cu): REAL FUNCTIONS, operands and result by value (the sm_100a ABI keeps all 24 words in registers, no
+//     stack traffic): the two bodies (~4 KB together) stay cache resident; costs ~17 % call-marshalling IMAD.MOVs
+//     (round 1 measured 38.9 M verifies/s for the curve kernel in this form).
 #if SV_DEVICE_CODE && !defined(SV_FE_INLINE)
 static __device__ __noinline__ fe fe_mul_fn(fe a, fe b) {
     u32 t[16];

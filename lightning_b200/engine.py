@@ -38,7 +38,7 @@ class SvTx(ctypes.Structure):
 class SvInfo(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("sm_count", ctypes.c_int), ("main_block", ctypes.c_int),
                 ("main_grid", ctypes.c_int), ("main_regs", ctypes.c_int), ("gtable_bytes", ctypes.c_size_t),
-                ("scratch_bytes", ctypes.c_size_t), ("launches", ctypes.c_ulonglong), ("l2_persist_bytes", ctypes.c_size_t)]
+                ("scratch_bytes", ctypes.c_size_t), ("launches", ctypes.c_ulonglong), ("l2_persist_bytes", ctypes.c_size_t), ("l2_max_persist_bytes", ctypes.c_size_t)]
 
 
 def load_library():
