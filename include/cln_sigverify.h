@@ -134,6 +134,12 @@ int sv_verify_schnorr_batch_host(sv_ctx *ctx, const uint8_t *msg32, const uint8_
 int sv_set_dedup(sv_ctx *ctx, int on);
 unsigned sv_last_distinct_keys(const sv_ctx *ctx);
 
+/* Compressed-key ECDSA (SV_KIND_ECDSA33) batches above the small-batch limit never take the square root of
+ * secp256k1_eckey_pubkey_parse (eckey_impl.h:17-20 -> group_impl.h:334-346): the unknown y only scales Z, the final
+ * comparison becomes linear in y and is settled by one batched division (lightning_b200/csrc/verify.cuh, "without the
+ * square root").  Verdicts are identical; sv_set_nosqrt(ctx, 0) selects the plain flow (A/B measurements, tests). */
+int sv_set_nosqrt(sv_ctx *ctx, int on);
+
 /* ---- n ECDSA signatures by ONE key (every HTLC signature of a commitment_signed is made
  *      with remote_htlckey, channeld/channeld.c:2154,2215-2232).  The key is decoded and its multiples table built once;
  *      each verification skips the per-signature square root and table build.  kind: SV_KIND_ECDSA33 or _XY; key is

@@ -146,7 +146,7 @@ template <int KIND>
 __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
     k_main(sv_work* work, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
            const ge_mem* __restrict__ gtab, qtab_entry* scratch, u8* __restrict__ verdict, u8* keyok) {
-    const size_t keylen = (KIND == SV_KIND_ECDSA33) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
+    const size_t keylen = (KIND == SV_KIND_ECDSA33 || KIND == SV_KIND_ECDSA33_NS) ? 33 : (KIND == SV_KIND_ECDSA_XY ? 64 : 32);
 #ifdef SV_COMB_SMEM
     // VARIANT: the 17 x 128-entry 8-bit comb (136 KiB) is staged in shared memory once per (persistent) CTA by ONE bulk
     // asynchronous copy (cp.async.bulk: the TMA engine, UBLKCP in SASS), completion signalled on an mbarrier
@@ -202,7 +202,12 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
         const size_t j = active ? i : 0;
 #endif
         const sv_work* w = active ? (work + i) : &g_idle_work;
-        if (KIND == SV_KIND_SCHNORR) {
+        if (KIND == SV_KIND_ECDSA33_NS) {
+            // compressed-key ECDSA without the square root: D, B, c parked in the work record, k_final_ecdsa33 decides
+            u32 code = ecdsa33_nosqrt_curve_side(w, key + keylen * j, sig + 64 * j, gtab, tab,
+                                                 reinterpret_cast<sv_ns_park*>(work + j), active, part);
+            if (active) verdict[i] = (u8)code;
+        } else if (KIND == SV_KIND_SCHNORR) {
             // park R in the work record; k_final_schnorr turns it into a verdict (batched inversion)
             bool ok = (w->flags & SV_WF_VALID) != 0;
             ge Q;
@@ -490,6 +495,16 @@ __global__ void __launch_bounds__(64) k_final_schnorr(const sv_work* work, const
     if (base >= n) return;
     int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
     schnorr_final_batch(verdict + base, reinterpret_cast<const sv_jac*>(work) + base, sig + 64 * base, cnt);
+}
+
+static_assert(sizeof(sv_ns_park) == sizeof(sv_work), "D, B, c are parked in place of the work record");
+__global__ void __launch_bounds__(64) k_final_ecdsa33(const sv_work* work, const u8* key33, const u8* sig, size_t n,
+                                                       const ge_mem* gtab, u8* verdict, u8* aux) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t base = t * SV_FINAL_BATCH;
+    if (base >= n) return;
+    int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
+    ecdsa33_nosqrt_final_batch(verdict + base, work + base, key33 + 33 * base, sig + 64 * base, gtab, cnt, aux ? aux + base : nullptr);
 }
 
 __global__ void k_pack_bitmap(const u8* verdict, size_t n, u32* bitmap) {
@@ -835,6 +850,7 @@ struct sv_ctx {
     u8 *dd_buf, *sk_buf;
     size_t dd_cap, sk_cap;
     int dedup;  // gossip batches: look for repeated keys (sv_set_dedup; default on)
+    int nosqrt; // compressed-key ECDSA through the flow without the square root (default on; env SV_NOSQRT=0: measurement aid)
     u32 last_distinct;
     // growable device staging for the host-buffer entry points
     size_t cap;  // items
@@ -961,6 +977,8 @@ extern "C" int sv_create(sv_ctx** out, int device) {
     ctx->dd_buf = ctx->sk_buf = nullptr;
     ctx->dd_cap = ctx->sk_cap = 0;
     ctx->dedup = 1;
+    ctx->nosqrt = 1;
+    if (const char* e = getenv("SV_NOSQRT")) ctx->nosqrt = atoi(e) != 0;
     ctx->last_distinct = 0;
     ctx->small_cap = SV_SMALL_CAP;
     ctx->small_max = SV_SMALL_MAX_DEFAULT;
@@ -1217,7 +1235,13 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
     size_t want = (n + SV_MAIN_BLOCK - 1) / SV_MAIN_BLOCK;
     unsigned grid = (unsigned)(want < (size_t)ctx->main_grid ? want : (size_t)ctx->main_grid);
-    if (kind == SV_KIND_ECDSA33)
+    if (kind == SV_KIND_ECDSA33 && ctx->nosqrt) {
+        // compressed keys: the flow that skips the square root (verify.cuh "without the square root")
+        k_main<SV_KIND_ECDSA33_NS><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, nullptr);
+        size_t threads = (n + SV_FINAL_BATCH - 1) / SV_FINAL_BATCH;
+        k_final_ecdsa33<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_keyok);
+        ctx->launches += 1;
+    } else if (kind == SV_KIND_ECDSA33)
         k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
     else if (kind == SV_KIND_ECDSA_XY)
         k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
@@ -1257,6 +1281,11 @@ extern "C" int sv_set_l2_policy(sv_ctx* ctx, int on) {
 extern "C" int sv_set_dedup(sv_ctx* ctx, int on) {
     if (!ctx) return SV_ERR_ARG;
     ctx->dedup = on ? 1 : 0;
+    return SV_OK;
+}
+extern "C" int sv_set_nosqrt(sv_ctx* ctx, int on) {
+    if (!ctx) return SV_ERR_ARG;
+    ctx->nosqrt = on ? 1 : 0;
     return SV_OK;
 }
 extern "C" unsigned sv_last_distinct_keys(const sv_ctx* ctx) { return ctx ? ctx->last_distinct : 0; }

@@ -30,6 +30,7 @@
 #define SV_KIND_ECDSA33 0   // msg32 | pub33 (02/03 || x) | sig64 (r||s)
 #define SV_KIND_ECDSA_XY 1  // msg32 | pubxy64 (x || y)   | sig64 (r||s)      (pre-decompressed key)
 #define SV_KIND_SCHNORR 2   // msg32 | xonly32            | sig64 (R.x||s)    BIP-340
+#define SV_KIND_ECDSA33_NS 3  // internal: kind 0 through the flow that never takes the square root (see below)
 
 // G comb table geometry: rows 0..14 hold d*B_i for d = 1..32768, row 15 holds d = 1..65536
 #define SV_GT_ROW 32768
@@ -294,10 +295,9 @@ SV_HD void qtable_fetch(ge& p, const qtab_entry* tab, u32 v, u32 sneg, bool lam)
     if (dneg ^ sneg) fe_neg(p.y, p.y);
 }
 
-// R = u1*G + u2*Q in true Jacobian coordinates.
-// R = u1*G + u2*Q given a ready odd-multiples table of Q (common Z = zc)
-SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qtab_entry* tab, const fe& zc,
-                         unsigned sync_threads = 0) {
+// R = u2*Q in true Jacobian coordinates, given a ready odd-multiples table of Q (common Z = zc): the joint ladder over
+// both GLV halves (128 doublings, 2 x 33 mixed additions)
+SV_HD void ecmult_ladder_q(gej& R, const sv_work* w, const qtab_entry* tab, const fe& zc, unsigned sync_threads = 0) {
     const u32* m1 = w->k1;
     const u32* m2 = w->k2;
     u32 t1 = m1[4], t2 = m2[4];
@@ -344,7 +344,11 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
     }
     // leave the scaled curve: true Z = Z * zc
     fe_mul(R.z, R.z, zc);
-    // fixed-base comb
+}
+
+// R += u1*G through the fixed-base comb (16 mixed additions against the 34 MiB table)
+SV_HD void ecmult_comb_add(gej& R, const sv_work* w, const ge_mem* gtab, unsigned sync_threads = 0) {
+    ge p;
 #if defined(SV_COMB_SMEM) && SV_DEVICE_CODE
     // VARIANT: 8-bit GLV comb against the 131 KB table staged in shared memory (k_main copies it in with one bulk copy):
     // 2 x 17 windows -> up to 34 mixed additions and a beta multiplication for each lambda-half point
@@ -389,6 +393,13 @@ SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qta
         }
     }
 #endif
+}
+
+// R = u1*G + u2*Q in true Jacobian coordinates
+SV_HD void ecmult_ladder(gej& R, const sv_work* w, const ge_mem* gtab, const qtab_entry* tab, const fe& zc,
+                         unsigned sync_threads = 0) {
+    ecmult_ladder_q(R, w, tab, zc, sync_threads);
+    ecmult_comb_add(R, w, gtab, sync_threads);
 }
 
 SV_HD void ecmult_uniform(gej& R, const sv_work* w, const ge& Q, const ge_mem* gtab, qtab_entry* tab,
@@ -528,6 +539,170 @@ SV_HD u32 verify_curve_side(int kind, const sv_work* w, const u8* key, const u8*
     ecmult_uniform(R, w, Q, gtab, tab, sync_threads);
     u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64) : ecdsa_final(R, sig64, flags);
     return ok ? v : 0u;
+}
+
+// ---- compressed-key ECDSA without the square root -------------------------------------------------------------------
+// Decompressing a 33-byte key costs a square root (254 squarings + 13 multiplications, 10 % of a verification).  It can be
+// traded for ~50 multiplications by never materialising y:  with c = x^3 + 7 and y the (unknown) root of c,
+//   * phi: (X, Y) -> (y^2 X, y^3 Y) maps the curve onto  E': Y^2 = X^3 + 7 c^3  and sends Q = (x, y) to Q' = (c x, c^2),
+//     which needs no y.  The doubling / addition formulas never use the curve constant, so table build and GLV ladder run
+//     on E' unchanged (the endomorphism is still X -> beta X) and give S' = u2*Q' = (X1, Y1, Zs);
+//   * pulled back, u2*Q = (X1, Y1, y*Zs) on the real curve: y only scales Z.  Adding T = u1*G = (X2, Y2, Z2) with the
+//     Jacobian addition formulas and collecting powers of y (y^2 = c) gives  X3 = A - y*B  and  Z3^2 = c*z3^2  with A, B,
+//     z3 free of y, so the ECDSA test  X3 == r * Z3^2  reads   y * B == A - r*c*z3^2 =: D ;
+//   * it is linear in y: the signature is valid iff  y = D/B  is THE root the key names, i.e. (D/B)^2 == c and the parity
+//     of D/B equals the prefix bit.  For an invalid key (c a non-residue) no value squares to c: verdict 0, as
+//     secp256k1_eckey_pubkey_parse refusing the key (eckey_impl.h:17-20, group_impl.h:334-346).
+// The division is batched in k_final_ecdsa33 (Montgomery's trick over 16 signatures).  Rare configurations the linear form
+// does not cover (u1*G or u2*Q at infinity, equal x coordinates, B == 0, the r + n candidate of ecdsa_impl.h:250-262) are
+// re-verified there by the plain path with the real square root, so verdicts stay bit-exact.
+#define SV_NS_PENDING 2u  // D, B, c parked: k_final_ecdsa33 decides
+#define SV_NS_EXACT 4u    // work record left intact: k_final_ecdsa33 runs the plain path
+struct alignas(16) sv_ns_park {
+    u32 d[8], b[8], c[8], pad[8];
+};
+
+// Curve side for one item.  Returns 0 (verdict 0 is final), SV_NS_PENDING (park filled) or SV_NS_EXACT.  `park` may alias w.
+SV_HD u32 ecdsa33_nosqrt_curve_side(const sv_work* w, const u8* key33, const u8* sig64, const ge_mem* gtab, qtab_entry* tab,
+                                    sv_ns_park* park, bool store, unsigned sync_threads = 0) {
+    const u32 flags = w->flags;
+    bool ok = (flags & SV_WF_VALID) != 0;
+    const u8 pfx = key33[0];
+    fe x, c, seven;
+    ok = (pfx == 2 || pfx == 3) && ok;       // eckey_impl.h:17
+    ok = fe_set_b32(x, key33 + 1) && ok;     // x < p  (group_impl.h:334 via fe_set_b32_limit)
+    fe_set_u32(seven, 7);
+    fe_sqr(c, x);
+    fe_mul(c, c, x);
+    fe_add(c, c, seven);
+    {
+        ge Qp;  // Q' = (c x, c^2) on E'
+        fe_mul(Qp.x, c, x);
+        fe_sqr(Qp.y, c);
+        fe zc;
+        qtable_build(tab, zc, Qp, sync_threads);
+        gej S;
+        ecmult_ladder_q(S, w, tab, zc, sync_threads);
+        // the table is dead: park S' there while the comb runs
+        fe_to_words(tab[0].x, S.x);
+        fe_to_words(tab[0].y, S.y);
+        fe_to_words(tab[0].h, S.z);
+        tab[1].x[0] = S.inf;
+    }
+    gej T;
+    T.inf = 1;
+    fe_set_zero(T.x);
+    fe_set_zero(T.y);
+    fe_set_zero(T.z);
+    ecmult_comb_add(T, w, gtab, sync_threads);
+    bool exact = T.inf || tab[1].x[0] != 0 || (flags & SV_WF_R_PLUS_N) != 0;
+    // c again (cheaper than keeping 8 registers alive across ladder and comb)
+    fe_set_b32(x, key33 + 1);
+    fe_sqr(c, x);
+    fe_mul(c, c, x);
+    fe_add(c, c, seven);
+    fe X1, Y1, Zs, z2z2, t, U1, S1, czs2, s2p, H, z3, A, B, HH, D;
+    fe_from_words(X1, tab[0].x);
+    fe_from_words(Y1, tab[0].y);
+    fe_from_words(Zs, tab[0].h);
+    fe_sqr(z2z2, T.z);
+    fe_mul(U1, X1, z2z2);            // U1 = X1 Z2^2
+    fe_mul(t, T.z, z2z2);
+    fe_mul(S1, Y1, t);               // S1 = Y1 Z2^3
+    fe_sqr(t, Zs);
+    fe_mul(czs2, c, t);              // (y Zs)^2
+    fe_mul(H, T.x, czs2);            // U2 = X2 (y Zs)^2
+    fe_sub(H, H, U1);                // H = U2 - U1
+    fe_mul(t, Zs, czs2);
+    fe_mul(s2p, T.y, t);             // S2 = y * s2p,  s2p = Y2 c Zs^3
+    exact = exact || fe_is_zero(H);  // equal x coordinates: doubling or infinity, depending on y
+    fe_mul(z3, H, Zs);
+    fe_mul(z3, z3, T.z);             // Z3 = y * z3
+    fe_mul(B, s2p, S1);
+    fe_dbl(B, B);                    // (S2 - S1)^2 = c s2p^2 + S1^2 - y * B
+    exact = exact || fe_is_zero(B);
+    fe_sqr(t, s2p);
+    fe_mul(A, c, t);
+    fe_sqr(t, S1);
+    fe_add(A, A, t);
+    fe_sqr(HH, H);
+    fe_mul(t, H, HH);
+    fe_sub(A, A, t);                 // - H^3
+    fe_mul(t, U1, HH);
+    fe_sub(A, A, t);
+    fe_sub(A, A, t);                 // - 2 U1 H^2 :  X3 = A - y B
+    fe_sqr(t, z3);
+    fe_mul(t, c, t);                 // Z3^2
+    fe rfe;
+    fe_set_b32(rfe, sig64);          // r < n < p
+    fe_mul(t, rfe, t);
+    fe_sub(D, A, t);                 // X3 == r Z3^2  <=>  y B == D
+    if (!ok) return 0u;
+    if (exact) return SV_NS_EXACT;
+    if (store) {
+        fe_to_words(park->d, D);
+        fe_to_words(park->b, B);
+        fe_to_words(park->c, c);
+    }
+    return SV_NS_PENDING;
+}
+
+// verdicts for cnt (<= SV_FINAL_BATCH) consecutive items; verdict[i] holds the code ecdsa33_nosqrt_curve_side returned
+// aux (optional, one byte per item): bit 0 = key decodes, bit 1 = signature encoding parsed — a valid signature proves its
+// key; only for the others (rare in honest traffic) is the key decoded with the real square root.
+SV_HD void ecdsa33_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8* key33, const u8* sig64, const ge_mem* gtab,
+                                      int cnt, u8* aux = nullptr) {
+    fe pre[SV_FINAL_BATCH];
+    fe acc, one;
+    fe_set_u32(one, 1);
+    for (int i = 0; i < cnt; i++) {
+        const sv_ns_park* pk = reinterpret_cast<const sv_ns_park*>(work + i);
+        fe b;
+        fe_from_words(b, pk->b);
+        if (verdict[i] != SV_NS_PENDING) b = one;
+        if (i == 0) pre[0] = b; else fe_mul(pre[i], pre[i - 1], b);
+    }
+    fe_inv(acc, pre[cnt - 1]);
+    for (int i = cnt - 1; i >= 0; i--) {
+        const sv_ns_park* pk = reinterpret_cast<const sv_ns_park*>(work + i);
+        const u32 code = verdict[i];
+        bool kd = false, need_kd = false;
+        fe b, bi;
+        fe_from_words(b, pk->b);
+        if (code != SV_NS_PENDING) b = one;
+        if (i > 0) {
+            fe_mul(bi, acc, pre[i - 1]);
+            fe_mul(acc, acc, b);
+        } else {
+            bi = acc;
+        }
+        if (code == SV_NS_PENDING) {
+            fe d, c, y, yy;
+            fe_from_words(d, pk->d);
+            fe_from_words(c, pk->c);
+            fe_mul(y, d, bi);
+            fe_normalize(y);
+            fe_sqr(yy, y);
+            bool good = fe_equal(yy, c) && (fe_is_odd(y) == (key33[33 * i] == 3));
+            verdict[i] = good ? 1 : 0;
+            kd = good;
+            need_kd = !good;
+        } else if (code == SV_NS_EXACT) {
+            qtab_entry tab[8];
+            verdict[i] = (u8)verify_curve_side(SV_KIND_ECDSA33, work + i, key33 + 33 * i, sig64 + 64 * i, gtab, tab, &kd);
+        } else {
+            verdict[i] = 0;
+            need_kd = true;
+        }
+        if (aux) {
+            if (need_kd) {
+                ge Q;
+                kd = key_decode(Q, SV_KIND_ECDSA33, key33 + 33 * i);
+            }
+            // the flags word of the work record lies past the parked D, B, c and is still intact
+            aux[i] = (u8)((kd ? 1u : 0u) | ((work[i].flags & SV_WF_PARSED) ? 2u : 0u));
+        }
+    }
 }
 
 // k*G (k != 0) as a normalised affine point through the fixed-base comb alone (signer of the synthetic workload generator,

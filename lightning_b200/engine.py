@@ -79,6 +79,7 @@ def load_library():
     lib.sv_verify_mixed_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]
     lib.sv_verify_schnorr_batch_host.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp]
     lib.sv_set_dedup.argtypes = [vp, i]
+    lib.sv_set_nosqrt.argtypes = [vp, i]
     lib.sv_last_distinct_keys.argtypes = [vp]
     lib.sv_last_distinct_keys.restype = ctypes.c_uint
     lib.sv_set_small_max.argtypes = [vp, sz]
@@ -257,6 +258,10 @@ class SigVerifier:
 
     def set_dedup(self, on=True):
         self._check(self.lib.sv_set_dedup(self._ctx, 1 if on else 0), "sv_set_dedup")
+
+    def set_nosqrt(self, on=True):
+        """compressed-key ECDSA batches: the flow without the square root (default) or the plain one"""
+        self._check(self.lib.sv_set_nosqrt(self._ctx, 1 if on else 0), "sv_set_nosqrt")
 
     def last_distinct_keys(self):
         return self.lib.sv_last_distinct_keys(self._ctx)

@@ -38,6 +38,9 @@ static inline void pair_swap(const pair_lane& L, fe& recv, const fe& send) {
 #include "../../lightning_b200/csrc/batch.cuh"
 
 static std::vector<ge_mem> g_table;
+static int g_ecdsa33_exact = 0;
+static size_t g_last_exact = 0;
+static u8* g_aux = nullptr;
 static std::vector<ge_mem> g_bases(16);
 
 static void build_gtable_fast() {
@@ -267,15 +270,15 @@ void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, si
         for (size_t base = 0; base < n; base += SV_PREP_BATCH) {
             int cnt = (int)((n - base < SV_PREP_BATCH) ? (n - base) : SV_PREP_BATCH);
             sc r[SV_PREP_BATCH], m[SV_PREP_BATCH], sv[SV_PREP_BATCH];
-            bool ok[SV_PREP_BATCH];
+            bool ok[SV_PREP_BATCH], parsed[SV_PREP_BATCH];
             for (int j = 0; j < cnt; j++) {
                 sc s;
-                ok[j] = ecdsa_parse(r[j], s, m[j], sig + 64 * (base + j), msg + 32 * (base + j), nullptr);
+                ok[j] = ecdsa_parse(r[j], s, m[j], sig + 64 * (base + j), msg + 32 * (base + j), &parsed[j]);
                 if (!ok[j]) { memset(s.v, 0, 32); s.v[0] = 1; }
                 sv[j] = s;
             }
             sc_batch_inverse(sv, cnt);
-            for (int j = 0; j < cnt; j++) ecdsa_finish_prep(work[base + j], ok[j], r[j], m[j], sv[j]);
+            for (int j = 0; j < cnt; j++) ecdsa_finish_prep(work[base + j], ok[j], r[j], m[j], sv[j], parsed[j]);
         }
     }
     qtab_entry tab[8];
@@ -294,7 +297,34 @@ void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, si
         }
         return;
     }
-    for (size_t i = 0; i < n; i++)
-        out[i] = (u8)verify_curve_side(kind, &work[i], key + keylen * i, sig + 64 * i, g_table.data(), tab);
+    if (kind == SV_KIND_ECDSA33 && !g_ecdsa33_exact) {  // as k_main<ECDSA33 without square root> + k_final_ecdsa33
+        size_t exact = 0;
+        for (size_t i = 0; i < n; i++) {
+            out[i] = (u8)ecdsa33_nosqrt_curve_side(&work[i], key + 33 * i, sig + 64 * i, g_table.data(), tab,
+                                                   reinterpret_cast<sv_ns_park*>(&work[i]), true);
+            exact += out[i] == SV_NS_EXACT;
+        }
+        g_last_exact = exact;
+        for (size_t base = 0; base < n; base += SV_FINAL_BATCH) {
+            int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
+            ecdsa33_nosqrt_final_batch(out + base, work.data() + base, key + 33 * base, sig + 64 * base, g_table.data(), cnt,
+                                       g_aux ? g_aux + base : nullptr);
+        }
+        return;
+    }
+    for (size_t i = 0; i < n; i++) {
+        bool kd;
+        out[i] = (u8)verify_curve_side(kind, &work[i], key + keylen * i, sig + 64 * i, g_table.data(), tab, &kd);
+        if (g_aux) g_aux[i] = (u8)((kd ? 1u : 0u) | ((work[i].flags & SV_WF_PARSED) ? 2u : 0u));  // as k_main
+    }
 }
+// ECDSA kinds, with the per-item byte the gossip path consumes: bit 0 = key decodes, bit 1 = r, s < n
+void emul_verify_batch_aux(int kind, const u8* msg, const u8* key, const u8* sig, size_t n, u8* out, u8* aux) {
+    g_aux = aux;
+    emul_verify_batch(kind, msg, key, sig, n, out);
+    g_aux = nullptr;
+}
+// kind ECDSA33: 1 = the plain path with the square root (what the engine runs when the caller wants the key-decoded flag)
+void emul_set_ecdsa33_exact(int on) { g_ecdsa33_exact = on; }
+size_t emul_last_exact_count(void) { return g_last_exact; }
 }

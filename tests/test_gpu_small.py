@@ -128,3 +128,43 @@ def test_small_path_composite_entry_points(engine, ref, cln, both):
     a, b = both(queue)
     want = np.array([util.ref_verify(ref, i % 3, w["msg"][i:i + 1], w[KINDS[i % 3][0]][i:i + 1], w[KINDS[i % 3][1]][i:i + 1])[0] for i in range(90)], np.uint8)
     assert np.array_equal(a, want) and np.array_equal(b, want)
+
+
+def test_ecdsa33_without_square_root_vs_plain_flow(engine, ref):
+    """Throughput kernels, compressed keys: the flow that never takes the square root (k_main<3> + k_final_ecdsa33, the
+    default) and the plain flow give the reference's verdicts on random/corrupted triples at ragged sizes, off-curve keys,
+    structured mutations, the crafted scalars that force the fall-back inside k_final_ecdsa33, and the tests.c edge cases."""
+    default = engine.small_max()
+    engine.set_small_max(0)
+    try:
+        w = util.corrupt(util.make_signed(ref, 5000, seed=78), every=4)
+        p = 2**256 - 2**32 - 977
+        for i in range(60):  # x not on the curve
+            x = int.from_bytes(bytes(w["pub33"][i, 1:]), "big")
+            while pow((pow(x, 3, p) + 7) % p, (p - 1) // 2, p) == 1:
+                x = (x + 1) % p
+            w["pub33"][i, 1:] = np.frombuffer(x.to_bytes(32, "big"), np.uint8)
+        w["pub33"][60, 0] = 4   # bad prefix
+        w["pub33"][61, 1:] = 255  # x >= p
+        want = util.ref_verify(ref, 0, w["msg"], w["pub33"], w["sig"], threads=4)
+        assert not want[:62].any() and want.sum() > 3000
+        m = util.make_signed(ref, 3000, seed=124)
+        mutations.mutate(m, seed=10)
+        mwant = util.ref_verify(ref, 0, m["msg"], m["pub33"], m["sig"], threads=4)
+        amsg, apub33, _, asig = adversarial.load()
+        cases = json.load(open(os.path.join(GOLD, "ecdsa_edge_cases.json")))
+        h = lambda s, k: np.frombuffer(bytes.fromhex(s), dtype=np.uint8).reshape(1, k)
+        cm = np.concatenate([h(c["msg32"], 32) for c in cases])
+        ck = np.concatenate([h(c["pub33"], 33) for c in cases])
+        cs = np.concatenate([h(c["sig64"], 64) for c in cases])
+        cwant = np.array([c["expected"] for c in cases], np.uint8)
+        for on in (True, False):
+            engine.set_nosqrt(on)
+            for n in (1, 15, 16, 17, 255, 256, 257, 4097, 5000):
+                assert np.array_equal(engine.verify(0, w["msg"][:n], w["pub33"][:n], w["sig"][:n]), want[:n]), (on, n)
+            assert np.array_equal(engine.verify(0, m["msg"], m["pub33"], m["sig"]), mwant), on
+            assert engine.verify(0, amsg, apub33, asig).all(), on
+            assert np.array_equal(engine.verify(0, cm, ck, cs), cwant), on
+    finally:
+        engine.set_nosqrt(True)
+        engine.set_small_max(default)

@@ -413,3 +413,49 @@ def test_bip340_batch_verification_group_equations(emul, ref):
             expect = [1, 1]
             expect[grp] = 0
             assert list(gok) == expect
+
+
+def test_ecdsa33_without_square_root_vs_plain_path(emul, ref):
+    """Compressed-key ECDSA has two flows in the engine (verify.cuh "without the square root"): the linear-in-y form with a
+    batched division, and the plain path with the real square root.  Both must give the reference's verdicts; random
+    workloads must stay on the fast flow, while the crafted scalars (u1*G = +-u2*Q, u1 = 0, r + n candidates) and keys whose
+    x is not on the curve are the cases the fast flow hands back."""
+    emul.emul_last_exact_count.restype = ctypes.c_size_t
+    w = util.corrupt(util.make_signed(ref, 600, seed=77), every=4)
+    # keys not on the curve (x^3 + 7 a non-residue), valid-looking otherwise
+    bad = w["pub33"][:50].copy()
+    for i in range(50):
+        x = int.from_bytes(bytes(bad[i, 1:]), "big")
+        while pow((pow(x, 3, p) + 7) % p, (p - 1) // 2, p) == 1:
+            x = (x + 1) % p
+        bad[i, 1:] = np.frombuffer(x.to_bytes(32, "big"), np.uint8)
+    w["pub33"][:50] = bad
+    want = util.ref_verify(ref, 0, w["msg"], w["pub33"], w["sig"])
+    assert not want[:50].any()
+    amsg, apub33, _, asig = adversarial.load()
+    awant = util.ref_verify(ref, 0, amsg, apub33, asig)
+    cases = json.load(open(os.path.join(GOLD, "ecdsa_edge_cases.json")))
+    h = lambda s, k: np.frombuffer(bytes.fromhex(s), dtype=np.uint8).reshape(1, k).copy()
+    try:
+        for exact in (0, 1):
+            emul.emul_set_ecdsa33_exact(exact)
+            assert np.array_equal(emul_verify(emul, 0, w["msg"], w["pub33"], w["sig"]), want), exact
+            if not exact:
+                assert emul.emul_last_exact_count() == 0  # nothing on a random workload needs the plain path
+            assert np.array_equal(emul_verify(emul, 0, amsg, apub33, asig), awant), exact
+            if not exact:
+                assert emul.emul_last_exact_count() > 0   # the crafted ones do
+            for c in cases:
+                assert emul_verify(emul, 0, h(c["msg32"], 32), h(c["pub33"], 33), h(c["sig64"], 64))[0] == c["expected"], (exact, c["name"])
+            # the per-item byte of the gossip path: bit 0 = the key parses (secp256k1_ec_pubkey_parse), bit 1 = r, s < n
+            n_items = w["msg"].shape[0]
+            out, aux = np.zeros(n_items, np.uint8), np.zeros(n_items, np.uint8)
+            emul.emul_verify_batch_aux(0, P(w["msg"]), P(w["pub33"]), P(w["sig"]), ctypes.c_size_t(n_items), P(out), P(aux))
+            assert np.array_equal(out, want)
+            tmp33, tmp64 = np.zeros(33, np.uint8), np.zeros(64, np.uint8)
+            for i in range(n_items):
+                kd = ref.ref_pubkey_convert(P(np.ascontiguousarray(w["pub33"][i])), ctypes.c_size_t(33), P(tmp33), P(tmp64))
+                ps = ref.ref_make_opaque_sig(P(np.ascontiguousarray(w["sig"][i])), P(tmp64))
+                assert aux[i] == (1 if kd else 0) | (2 if ps else 0), (exact, i, aux[i], kd, ps)
+    finally:
+        emul.emul_set_ecdsa33_exact(0)
