@@ -38,10 +38,14 @@ N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 BATCH = 1_000_000
 IMAD_PER_VERIFY = 125_440  # 1,960 field mults x 64
 BYTES_PER_VERIFY = 129.125
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_main<ECDSA33> launch over 1,000,000 verifications, from
-# `ncu --set full` (profiles/r1_k_main_1M_ncu_raw.csv): 766.8 MB + 562.9 MB.  ~10x the algorithmic 129 MB: the per-thread
-# Q-table slabs (768 B written + re-read per verification) and the 128-byte work records cycle through L2.
-NCU_DRAM_BYTES_PER_1M_LAUNCH = 766_794_752 + 562_898_944
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE curve-kernel launch over 1,000,000 verifications, from `ncu --set full`
+# (round 2: 724.9 MB + 311.6 MB; round 1 was 766.8 + 562.9 MB).  Algorithmic traffic is 0.32 GB (161 B of input, the 128-byte
+# work record in and out, the verdict); the rest are the comb's random 64-byte reads out of a 34 MiB table and the part of
+# the per-thread Q-table slabs that the L2 access-policy window cannot hold.
+NCU_DRAM_BYTES_PER_1M_LAUNCH = 724_892_672 + 311_600_384  # dram__bytes_read + _write, profiles/r2_k_main_nosqrt_ncu_summary.md
+# IMAD.WIDE.U32 the shipped curve kernel EXECUTES per verification (ncu, profiles/r2_k_main_nosqrt_dynamic_opmix.txt:
+# 3,571,030,146 warp instructions x 32 lanes / 1,000,000): the flow without the square root does less than SURVEY's 125,440
+EXECUTED_IMAD_PER_VERIFY = 114_273
 METRIC = "secp256k1 verifies/sec"
 
 
@@ -512,9 +516,12 @@ def run_engine(args):
         "clocks": clocks,
         "roofline": {"bound": "integer (IMAD.WIDE.U32 issue)", "achieved": achieved / 1e9, "peak": peak_imad / 1e9,
                      "unit": "GIMAD/s", "frac": achieved / peak_imad,
-                     "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if n == 1_000_000 else None, "traffic_unit": "bytes/launch (ncu, profiles/r1_k_main_1M_ncu_raw.csv)",
-                     "kernel": "k_main<ECDSA33>", "kernel_ms": main_avg, "prep_kernel_ms": prep_avg,
+                     "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if n == 1_000_000 else None, "traffic_unit": "bytes/launch (ncu, profiles/r2_k_main_nosqrt_ncu_raw.csv)",
+                     "kernel": "k_main<3> + k_final_ecdsa33 (compressed keys, no square root)", "kernel_ms": main_avg, "prep_kernel_ms": prep_avg,
                      "algorithmic_imad_per_verify": IMAD_PER_VERIFY,
+                     "executed_imad_per_verify": EXECUTED_IMAD_PER_VERIFY if os.environ.get("SV_NOSQRT", "1") != "0" else IMAD_PER_VERIFY,
+                     "pipe_frac": n * (EXECUTED_IMAD_PER_VERIFY if os.environ.get("SV_NOSQRT", "1") != "0" else IMAD_PER_VERIFY) / (main_avg * 1e-3) / peak_imad,
+                     "note": "frac = SURVEY 8(d)'s algorithmic 125,440 IMAD/verify over the kernel time; pipe_frac = multiplies actually issued (the shipped flow skips the key's square root)",
                      "peak_source": "measured live: engine probe k_probe_imad_wide (independent IMAD.WIDE.U32 chains)"},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if n == 1_000_000 else None,

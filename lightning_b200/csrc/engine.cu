@@ -207,6 +207,10 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
             u32 code = ecdsa33_nosqrt_curve_side(w, key + keylen * j, sig + 64 * j, gtab, tab,
                                                  reinterpret_cast<sv_ns_park*>(work + j), active, part);
             if (active) verdict[i] = (u8)code;
+        } else if (KIND == SV_KIND_SCHNORR_NS) {
+            u32 code = schnorr_nosqrt_curve_side(w, key + keylen * j, sig + 64 * j, gtab, tab,
+                                                 reinterpret_cast<sv_ns_park_schnorr*>(work + j), active, part);
+            if (active) verdict[i] = (u8)code;
         } else if (KIND == SV_KIND_SCHNORR) {
             // park R in the work record; k_final_schnorr turns it into a verdict (batched inversion)
             bool ok = (w->flags & SV_WF_VALID) != 0;
@@ -505,6 +509,16 @@ __global__ void __launch_bounds__(64) k_final_ecdsa33(const sv_work* work, const
     if (base >= n) return;
     int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
     ecdsa33_nosqrt_final_batch(verdict + base, work + base, key33 + 33 * base, sig + 64 * base, gtab, cnt, aux ? aux + base : nullptr);
+}
+
+static_assert(sizeof(sv_ns_park_schnorr) == sizeof(sv_work), "D, B, N, CG are parked in place of the work record");
+__global__ void __launch_bounds__(64) k_final_schnorr_ns(const sv_work* work, const u8* xonly32, const u8* sig, size_t n,
+                                                          const ge_mem* gtab, u8* verdict) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t base = t * SV_FINAL_BATCH;
+    if (base >= n) return;
+    int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
+    schnorr_nosqrt_final_batch(verdict + base, work + base, xonly32 + 32 * base, sig + 64 * base, gtab, cnt);
 }
 
 __global__ void k_pack_bitmap(const u8* verdict, size_t n, u32* bitmap) {
@@ -1245,8 +1259,12 @@ static int launch_verify(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key
         k_main<SV_KIND_ECDSA33><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
     else if (kind == SV_KIND_ECDSA_XY)
         k_main<SV_KIND_ECDSA_XY><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
-    else
-    {
+    else if (ctx->nosqrt) {
+        k_main<SV_KIND_SCHNORR_NS><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, nullptr);
+        size_t threads = (n + SV_FINAL_BATCH - 1) / SV_FINAL_BATCH;
+        k_final_schnorr_ns<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(work, d_key, d_sig, n, ctx->d_gtab, d_verdict);
+        ctx->launches += 1;
+    } else {
         k_main<SV_KIND_SCHNORR><<<grid, SV_MAIN_BLOCK, SV_MAIN_SMEM, st>>>(work, d_key, d_sig, n, ctx->d_gtab, sl->d_scratch, d_verdict, d_keyok);
         size_t threads = (n + SV_FINAL_BATCH - 1) / SV_FINAL_BATCH;
         k_final_schnorr<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(work, d_sig, n, d_verdict);

@@ -31,6 +31,7 @@
 #define SV_KIND_ECDSA_XY 1  // msg32 | pubxy64 (x || y)   | sig64 (r||s)      (pre-decompressed key)
 #define SV_KIND_SCHNORR 2   // msg32 | xonly32            | sig64 (R.x||s)    BIP-340
 #define SV_KIND_ECDSA33_NS 3  // internal: kind 0 through the flow that never takes the square root (see below)
+#define SV_KIND_SCHNORR_NS 4  // internal: kind 2 likewise
 
 // G comb table geometry: rows 0..14 hold d*B_i for d = 1..32768, row 15 holds d = 1..65536
 #define SV_GT_ROW 32768
@@ -701,6 +702,177 @@ SV_HD void ecdsa33_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8
             }
             // the flags word of the work record lies past the parked D, B, c and is still intact
             aux[i] = (u8)((kd ? 1u : 0u) | ((work[i].flags & SV_WF_PARSED) ? 2u : 0u));
+        }
+    }
+}
+
+// ---- BIP-340 without the square root ---------------------------------------------------------------------------------
+// Same idea for x-only keys: P = lift_x(px) is the point with the EVEN root y of c = px^3 + 7 (extrakeys/main_impl.h:32-38),
+// R = s*G - e*P must be finite with even y and x(R) == r (schnorrsig/main_impl.h:255-264).  With S = -e*P = (X1, Y1, y Zs) and
+// T = s*G the sum has  X3 = A - y B,  Y3 = E + y F,  Z3 = y z3  (y^2 = c folded in), so
+//     x(R) == r   <=>  y = D / B,  D = A - r c z3^2          and then     y(R) = (E B + F D) / (D c z3^3).
+// k_main parks D, B, N = E B + F D and CG = c z3^3; k_final_schnorr_ns inverts B * D * CG once per signature (batched) and
+// checks  (D/B)^2 == c,  D/B even,  N / (D CG) even.  Configurations outside the linear form go to the plain path.
+struct alignas(16) sv_ns_park_schnorr {
+    u32 d[8], b[8], n[8], cg[8];
+};
+
+SV_HD u32 schnorr_nosqrt_curve_side(const sv_work* w, const u8* xonly32, const u8* sig64, const ge_mem* gtab, qtab_entry* tab,
+                                    sv_ns_park_schnorr* park, bool store, unsigned sync_threads = 0) {
+    const u32 flags = w->flags;
+    bool ok = (flags & SV_WF_VALID) != 0;
+    fe x, c, seven;
+    ok = fe_set_b32(x, xonly32) && ok;  // px < p  (extrakeys/main_impl.h:32)
+    fe_set_u32(seven, 7);
+    fe_sqr(c, x);
+    fe_mul(c, c, x);
+    fe_add(c, c, seven);
+    {
+        ge Qp;
+        fe_mul(Qp.x, c, x);
+        fe_sqr(Qp.y, c);
+        fe zc;
+        qtable_build(tab, zc, Qp, sync_threads);
+        gej S;
+        ecmult_ladder_q(S, w, tab, zc, sync_threads);
+        fe_to_words(tab[0].x, S.x);
+        fe_to_words(tab[0].y, S.y);
+        fe_to_words(tab[0].h, S.z);
+        tab[1].x[0] = S.inf;
+    }
+    gej T;
+    T.inf = 1;
+    fe_set_zero(T.x);
+    fe_set_zero(T.y);
+    fe_set_zero(T.z);
+    ecmult_comb_add(T, w, gtab, sync_threads);
+    bool exact = T.inf || tab[1].x[0] != 0;
+    fe_set_b32(x, xonly32);
+    fe_sqr(c, x);
+    fe_mul(c, c, x);
+    fe_add(c, c, seven);
+    fe X1, Y1, Zs, z2z2, t, U1, S1, czs2, s2p, H, z3, A, B, HH, D, V, K, E, F, W0;
+    fe_from_words(X1, tab[0].x);
+    fe_from_words(Y1, tab[0].y);
+    fe_from_words(Zs, tab[0].h);
+    fe_sqr(z2z2, T.z);
+    fe_mul(U1, X1, z2z2);
+    fe_mul(t, T.z, z2z2);
+    fe_mul(S1, Y1, t);
+    fe_sqr(t, Zs);
+    fe_mul(czs2, c, t);
+    fe_mul(H, T.x, czs2);
+    fe_sub(H, H, U1);
+    fe_mul(t, Zs, czs2);
+    fe_mul(s2p, T.y, t);
+    exact = exact || fe_is_zero(H);
+    fe_mul(z3, H, Zs);
+    fe_mul(z3, z3, T.z);
+    fe_mul(F, s2p, S1);              // s2p S1 (kept: F needs S1 * B = 2 S1 * this)
+    fe_dbl(B, F);
+    exact = exact || fe_is_zero(B);
+    fe_sqr(t, s2p);
+    fe_mul(A, c, t);
+    fe_sqr(t, S1);
+    fe_add(A, A, t);
+    fe_sqr(HH, H);
+    fe_mul(K, H, HH);                // H^3
+    fe_sub(A, A, K);
+    fe_mul(V, U1, HH);
+    fe_sub(A, A, V);
+    fe_sub(A, A, V);                 // X3 = A - y B
+    fe_mul(K, K, S1);                // K = S1 H^3
+    fe_sub(V, V, A);                 // V - A
+    // Y3 = (y s2p - S1)(V - X3) - K = E + y F
+    fe_mul(E, c, s2p);
+    fe_mul(E, E, B);
+    fe_mul(t, S1, V);
+    fe_sub(E, E, t);
+    fe_sub(E, E, K);                 // E = c s2p B - S1 (V - A) - K
+    fe_mul(F, s2p, V);
+    fe_mul(t, S1, B);
+    fe_sub(F, F, t);                 // F = s2p (V - A) - S1 B
+    fe_sqr(t, z3);
+    fe_mul(W0, c, t);                // Z3^2 = c z3^2
+    fe rfe;
+    fe_set_b32(rfe, sig64);          // r < p checked by the scalar side (flags)
+    fe_mul(t, rfe, W0);
+    fe_sub(D, A, t);                 // y B == D
+    fe_mul(E, E, B);
+    fe_mul(F, F, D);
+    fe_add(E, E, F);                 // N = E B + F D
+    fe_mul(W0, W0, z3);              // CG = c z3^3
+    if (!ok) return 0u;
+    if (exact) return SV_NS_EXACT;
+    if (store) {
+        fe_to_words(park->d, D);
+        fe_to_words(park->b, B);
+        fe_to_words(park->n, E);
+        fe_to_words(park->cg, W0);
+    }
+    return SV_NS_PENDING;
+}
+
+SV_HD void schnorr_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8* xonly32, const u8* sig64, const ge_mem* gtab,
+                                      int cnt) {
+    fe pre[SV_FINAL_BATCH];
+    fe acc, one;
+    fe_set_u32(one, 1);
+    for (int i = 0; i < cnt; i++) {
+        const sv_ns_park_schnorr* pk = reinterpret_cast<const sv_ns_park_schnorr*>(work + i);
+        fe v = one;
+        if (verdict[i] == SV_NS_PENDING) {
+            fe d, b, cg;
+            fe_from_words(d, pk->d);
+            fe_from_words(b, pk->b);
+            fe_from_words(cg, pk->cg);
+            fe_mul(v, d, cg);
+            fe_mul(v, v, b);      // B * D * CG
+            if (fe_is_zero(v)) v = one;  // D == 0 (B, CG are non-zero here): y would be 0, never a root of c != 0 -> rejected below
+        }
+        if (i == 0) pre[0] = v; else fe_mul(pre[i], pre[i - 1], v);
+    }
+    fe_inv(acc, pre[cnt - 1]);
+    for (int i = cnt - 1; i >= 0; i--) {
+        const sv_ns_park_schnorr* pk = reinterpret_cast<const sv_ns_park_schnorr*>(work + i);
+        const u32 code = verdict[i];
+        fe d, b, cg, w, v = one, vi;
+        if (code == SV_NS_PENDING) {
+            fe_from_words(d, pk->d);
+            fe_from_words(b, pk->b);
+            fe_from_words(cg, pk->cg);
+            fe_mul(w, d, cg);     // W = D CG
+            fe_mul(v, w, b);
+            if (fe_is_zero(v)) v = one;
+        }
+        if (i > 0) {
+            fe_mul(vi, acc, pre[i - 1]);
+            fe_mul(acc, acc, v);
+        } else {
+            vi = acc;
+        }
+        if (code == SV_NS_PENDING) {
+            fe x, c, seven, y, yy, yr, nn, t;
+            fe_set_b32(x, xonly32 + 32 * i);
+            fe_set_u32(seven, 7);
+            fe_sqr(c, x);
+            fe_mul(c, c, x);
+            fe_add(c, c, seven);
+            fe_mul(t, w, vi);     // 1 / B
+            fe_mul(y, d, t);      // y = D / B
+            fe_normalize(y);
+            fe_sqr(yy, y);
+            fe_mul(t, b, vi);     // 1 / W
+            fe_from_words(nn, pk->n);
+            fe_mul(yr, nn, t);    // y(R) = N / W
+            fe_normalize(yr);
+            bool good = !fe_is_zero(d) && fe_equal(yy, c) && !fe_is_odd(y) && !fe_is_odd(yr);
+            verdict[i] = good ? 1 : 0;
+        } else if (code == SV_NS_EXACT) {
+            qtab_entry tab[8];
+            verdict[i] = (u8)verify_curve_side(SV_KIND_SCHNORR, work + i, xonly32 + 32 * i, sig64 + 64 * i, gtab, tab);
+        } else {
+            verdict[i] = 0;
         }
     }
 }

@@ -282,6 +282,20 @@ void emul_verify_batch(int kind, const u8* msg, const u8* key, const u8* sig, si
         }
     }
     qtab_entry tab[8];
+    if (kind == SV_KIND_SCHNORR && !g_ecdsa33_exact) {  // as k_main<BIP-340 without square root> + k_final_schnorr_ns
+        size_t exact = 0;
+        for (size_t i = 0; i < n; i++) {
+            out[i] = (u8)schnorr_nosqrt_curve_side(&work[i], key + 32 * i, sig + 64 * i, g_table.data(), tab,
+                                                   reinterpret_cast<sv_ns_park_schnorr*>(&work[i]), true);
+            exact += out[i] == SV_NS_EXACT;
+        }
+        g_last_exact = exact;
+        for (size_t base = 0; base < n; base += SV_FINAL_BATCH) {
+            int cnt = (int)((n - base < SV_FINAL_BATCH) ? (n - base) : SV_FINAL_BATCH);
+            schnorr_nosqrt_final_batch(out + base, work.data() + base, key + 32 * base, sig + 64 * base, g_table.data(), cnt);
+        }
+        return;
+    }
     if (kind == SV_KIND_SCHNORR) {  // as k_main<SCHNORR> + k_final_schnorr: park R, then batched inversion
         for (size_t i = 0; i < n; i++) {
             bool ok = (work[i].flags & SV_WF_VALID) != 0;
@@ -324,7 +338,7 @@ void emul_verify_batch_aux(int kind, const u8* msg, const u8* key, const u8* sig
     emul_verify_batch(kind, msg, key, sig, n, out);
     g_aux = nullptr;
 }
-// kind ECDSA33: 1 = the plain path with the square root (what the engine runs when the caller wants the key-decoded flag)
+// kinds ECDSA33 and SCHNORR: 1 = the plain flow with the square root, 0 = the flow without it (the engine's default)
 void emul_set_ecdsa33_exact(int on) { g_ecdsa33_exact = on; }
 size_t emul_last_exact_count(void) { return g_last_exact; }
 }

@@ -131,9 +131,10 @@ def test_small_path_composite_entry_points(engine, ref, cln, both):
 
 
 def test_ecdsa33_without_square_root_vs_plain_flow(engine, ref):
-    """Throughput kernels, compressed keys: the flow that never takes the square root (k_main<3> + k_final_ecdsa33, the
-    default) and the plain flow give the reference's verdicts on random/corrupted triples at ragged sizes, off-curve keys,
-    structured mutations, the crafted scalars that force the fall-back inside k_final_ecdsa33, and the tests.c edge cases."""
+    """Throughput kernels, compressed and x-only keys: the flow that never takes the square root (k_main<3> + k_final_ecdsa33,
+    k_main<4> + k_final_schnorr_ns; the default) and the plain flow give the reference's verdicts on random/corrupted triples
+    at ragged sizes, off-curve keys, structured mutations, the crafted scalars that force the fall-back inside the final
+    kernel, the tests.c edge cases and the BIP-340 vectors."""
     default = engine.small_max()
     engine.set_small_max(0)
     try:
@@ -158,6 +159,16 @@ def test_ecdsa33_without_square_root_vs_plain_flow(engine, ref):
         ck = np.concatenate([h(c["pub33"], 33) for c in cases])
         cs = np.concatenate([h(c["sig64"], 64) for c in cases])
         cwant = np.array([c["expected"] for c in cases], np.uint8)
+        ws = util.corrupt(util.make_signed(ref, 5000, seed=79), every=3)
+        ws["xonly"][:60] = w["pub33"][:60, 1:]   # x-only keys off the curve
+        ws["ssig"][60:80, 32:] = 0               # s = 0: the comb sum is the point at infinity
+        swant = util.ref_verify(ref, 2, ws["msg"], ws["xonly"], ws["ssig"], threads=4)
+        assert not swant[:80].any() and swant.sum() > 2000
+        vecs = json.load(open(os.path.join(GOLD, "bip340.json")))
+        bm = np.concatenate([h(v["msg32"], 32) for v in vecs])
+        bk = np.concatenate([h(v["xonly"], 32) for v in vecs])
+        bs = np.concatenate([h(v["sig64"], 64) for v in vecs])
+        bwant = np.array([v["expected"] for v in vecs], np.uint8)
         for on in (True, False):
             engine.set_nosqrt(on)
             for n in (1, 15, 16, 17, 255, 256, 257, 4097, 5000):
@@ -165,6 +176,9 @@ def test_ecdsa33_without_square_root_vs_plain_flow(engine, ref):
             assert np.array_equal(engine.verify(0, m["msg"], m["pub33"], m["sig"]), mwant), on
             assert engine.verify(0, amsg, apub33, asig).all(), on
             assert np.array_equal(engine.verify(0, cm, ck, cs), cwant), on
+            for n in (1, 16, 17, 4097, 5000):  # BIP-340 takes the same switch
+                assert np.array_equal(engine.verify(2, ws["msg"][:n], ws["xonly"][:n], ws["ssig"][:n]), swant[:n]), (on, n)
+            assert np.array_equal(engine.verify(2, bm, bk, bs), bwant), on
     finally:
         engine.set_nosqrt(True)
         engine.set_small_max(default)

@@ -457,5 +457,17 @@ def test_ecdsa33_without_square_root_vs_plain_path(emul, ref):
                 kd = ref.ref_pubkey_convert(P(np.ascontiguousarray(w["pub33"][i])), ctypes.c_size_t(33), P(tmp33), P(tmp64))
                 ps = ref.ref_make_opaque_sig(P(np.ascontiguousarray(w["sig"][i])), P(tmp64))
                 assert aux[i] == (1 if kd else 0) | (2 if ps else 0), (exact, i, aux[i], kd, ps)
+            # BIP-340 through the same switch: random / corrupted triples, x-only keys off the curve, s = 0 (the comb sum is
+            # the point at infinity: handed to the plain flow), and the official vectors
+            ws = util.corrupt(util.make_signed(ref, 400, seed=79), every=3)
+            ws["xonly"][:40] = w["pub33"][:40, 1:]   # off the curve
+            ws["ssig"][40:50, 32:] = 0               # s = 0
+            swant = util.ref_verify(ref, 2, ws["msg"], ws["xonly"], ws["ssig"])
+            assert not swant[:50].any() and swant.sum() > 150
+            assert np.array_equal(emul_verify(emul, 2, ws["msg"], ws["xonly"], ws["ssig"]), swant), exact
+            if not exact:
+                assert emul.emul_last_exact_count() == 10
+            for v in json.load(open(os.path.join(GOLD, "bip340.json"))):
+                assert emul_verify(emul, 2, h(v["msg32"], 32), h(v["xonly"], 32), h(v["sig64"], 64))[0] == v["expected"], (exact, v["index"])
     finally:
         emul.emul_set_ecdsa33_exact(0)
