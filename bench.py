@@ -320,27 +320,43 @@ def run_engine(args):
             eng.sync(sh)
             bad = corrupt_on_device(torch, msg, key, sig)
         batches.append((msg, key, sig, bad))
-    # per-stream outputs (two steps may be in flight)
-    verdicts = [torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(2)]
-    bitmaps = [torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev) for _ in range(2)]
-    gathereds = [torch.zeros(world * bitmaps[0].numel(), dtype=torch.int32, device=dev) if world > 1 else None for _ in range(2)]
+    # Output sets (verdict bytes, bitmap, gathered bitmap), NOUT deep.  Two steps may be computing, and with N > 1 the
+    # gather of a finished step must not hold up the launch streams: the NCCL kernel only gets an SM when a CTA of the
+    # persistent curve kernel retires, so a launch stream that waited for "its" gather would idle through most of the other
+    # stream's batch (measured at N = 2: 49.9 M/s per GPU instead of 53).  The gather therefore runs on a stream of its own
+    # behind an event, and a launch stream only waits for the gather that read its output set NOUT steps earlier.
+    NOUT = 4
+    verdicts = [torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(NOUT)]
+    bitmaps = [torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev) for _ in range(NOUT)]
+    gathereds = [torch.zeros(world * bitmaps[0].numel(), dtype=torch.int32, device=dev) if world > 1 else None for _ in range(NOUT)]
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    gathered_ev = [None] * NOUT
     verdict, bitmap = verdicts[0], bitmaps[0]
     torch.cuda.synchronize()
 
     def step(i, single=False):
         j = 0 if single else (i & 1)
+        o = 0 if single else (i % NOUT)
+        st = streams[j]
         msg, key, sig, _ = batches[i & 1]
-        eng.verify_device(kind, msg.data_ptr(), key.data_ptr(), sig.data_ptr(), n, verdicts[j].data_ptr(),
-                          bitmaps[j].data_ptr(), streams[j].cuda_stream)
+        if world > 1 and gathered_ev[o] is not None:
+            st.wait_event(gathered_ev[o])  # bitmaps[o] is about to be overwritten
+        eng.verify_device(kind, msg.data_ptr(), key.data_ptr(), sig.data_ptr(), n, verdicts[o].data_ptr(),
+                          bitmaps[o].data_ptr(), st.cuda_stream)
         if world > 1:  # the only exchange step of the path: gather the verdict bitmap over NVLink
-            with torch.cuda.stream(streams[j]):
-                dist.all_gather_into_tensor(gathereds[j], bitmaps[j])
+            ev = torch.cuda.Event()
+            ev.record(st)
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(gathereds[o], bitmaps[o])
+            gathered_ev[o] = torch.cuda.Event()
+            gathered_ev[o].record(comm)
 
     def join_streams():
-        """make streams[0] wait for everything queued on streams[1]"""
-        if streams[1] is not streams[0]:
+        """make streams[0] wait for everything queued on streams[1] and on the gather stream"""
+        for other in ([streams[1]] if streams[1] is not streams[0] else []) + ([comm] if comm is not None else []):
             ev = torch.cuda.Event()
-            ev.record(streams[1])
+            ev.record(other)
             streams[0].wait_event(ev)
 
     def fork_streams():
@@ -666,6 +682,8 @@ def run_c4(args):
     from concurrent.futures import ThreadPoolExecutor
     eng = L.SigVerifier(0)
     eng.set_profiling(True)
+    if os.environ.get("SV_BENCH_NODEDUP"):  # measurement aid: every signature decodes its own key
+        eng.set_dedup(False)
     base = load_gossip_store()
     chans = {}
     for m in base:
