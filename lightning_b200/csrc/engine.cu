@@ -1028,6 +1028,12 @@ extern "C" int sv_create(sv_ctx** out, int device) {
         CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_main<SV_KIND_ECDSA33>, SV_MAIN_BLOCK, SV_MAIN_SMEM));
         if (occ < 1) occ = 1;
         ctx->main_grid = ctx->sm_count * occ;
+        // measurement aid: leave a few CTA slots of the persistent curve kernel free (e.g. for a collective's kernel that
+        // becomes ready while the grid is resident)
+        if (const char* e = getenv("SV_MAIN_GRID_RESERVE")) {
+            int r = atoi(e);
+            if (r > 0 && r < ctx->main_grid) ctx->main_grid -= r;
+        }
         ctx->scratch_bytes = (size_t)ctx->main_grid * SV_MAIN_BLOCK * 8 * sizeof(qtab_entry);
         {
             size_t gt = ((size_t)SV_GT_ENTRIES * sizeof(ge_mem) + 255) & ~(size_t)255;
@@ -1369,7 +1375,8 @@ extern "C" int sv_verify_host(sv_ctx* ctx, int kind, const uint8_t* msg32, const
     // Software pipeline inside a chunk: slices sized in whole waves of the persistent grid; slice k+1 is copied on
     // the copy stream while slice k runs; consecutive slices alternate between the two compute streams (each has its own
     // launch slot), so the partially filled last wave of one slice overlaps the next slice.  First slice small so the
-    // kernels start early.
+    // kernels start early — and it also takes the odd remainder of the chunk: its thin last wave is covered by the second
+    // slice, and the LAST slice (whose tail nothing can cover: the call is synchronous) ends on a full wave.
     const size_t wave = (size_t)ctx->main_grid * SV_MAIN_BLOCK;
     for (size_t off = 0; off < n; off += chunk) {
         size_t c = (n - off < chunk) ? (n - off) : chunk;
@@ -1377,8 +1384,8 @@ extern "C" int sv_verify_host(sv_ctx* ctx, int kind, const uint8_t* msg32, const
         int k = 0;
         const bool piped = c > 2 * wave;
         while (done < c) {
-            size_t want = (k == 0) ? 2 * wave : 6 * wave;
-            size_t s = (c - done < want + wave) ? (c - done) : want;  // do not leave a sliver behind
+            size_t want = (k == 0) ? wave + c % wave : 6 * wave;
+            size_t s = (c - done <= want + 2 * wave) ? (c - done) : want;  // do not leave a sliver behind
             if (k >= 7) s = c - done;
             cudaStream_t cs = piped ? ctx->copy_stream : ctx->stream;
             cudaStream_t ks = (piped && (k & 1)) ? ctx->stream2 : ctx->stream;

@@ -664,10 +664,13 @@ SV_HD void ecdsa33_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8
         if (i == 0) pre[0] = b; else fe_mul(pre[i], pre[i - 1], b);
     }
     fe_inv(acc, pre[cnt - 1]);
+    // Items that need the real square root after all are only noted here and worked off in loops of their own below: the
+    // lanes of a warp then run that (long) code side by side, whichever of their 16 items it concerns, instead of once per
+    // loop index in which any lane needs it.
+    u32 todo_key = 0, todo_exact = 0;
     for (int i = cnt - 1; i >= 0; i--) {
         const sv_ns_park* pk = reinterpret_cast<const sv_ns_park*>(work + i);
         const u32 code = verdict[i];
-        bool kd = false, need_kd = false;
         fe b, bi;
         fe_from_words(b, pk->b);
         if (code != SV_NS_PENDING) b = one;
@@ -677,6 +680,8 @@ SV_HD void ecdsa33_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8
         } else {
             bi = acc;
         }
+        // the flags word of the work record lies past the parked D, B, c and is still intact
+        const u32 parsed = (work[i].flags & SV_WF_PARSED) ? 2u : 0u;
         if (code == SV_NS_PENDING) {
             fe d, c, y, yy;
             fe_from_words(d, pk->d);
@@ -686,23 +691,31 @@ SV_HD void ecdsa33_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8
             fe_sqr(yy, y);
             bool good = fe_equal(yy, c) && (fe_is_odd(y) == (key33[33 * i] == 3));
             verdict[i] = good ? 1 : 0;
-            kd = good;
-            need_kd = !good;
+            if (aux) aux[i] = (u8)(1u | parsed);  // a valid signature proves its key
+            if (!good) todo_key |= 1u << i;
         } else if (code == SV_NS_EXACT) {
-            qtab_entry tab[8];
-            verdict[i] = (u8)verify_curve_side(SV_KIND_ECDSA33, work + i, key33 + 33 * i, sig64 + 64 * i, gtab, tab, &kd);
+            todo_exact |= 1u << i;
         } else {
             verdict[i] = 0;
-            need_kd = true;
+            todo_key |= 1u << i;
         }
-        if (aux) {
-            if (need_kd) {
-                ge Q;
-                kd = key_decode(Q, SV_KIND_ECDSA33, key33 + 33 * i);
-            }
-            // the flags word of the work record lies past the parked D, B, c and is still intact
-            aux[i] = (u8)((kd ? 1u : 0u) | ((work[i].flags & SV_WF_PARSED) ? 2u : 0u));
-        }
+    }
+    while (todo_exact) {
+        int i = 0;
+        while (!((todo_exact >> i) & 1u)) i++;
+        todo_exact &= todo_exact - 1u;
+        qtab_entry tab[8];
+        bool kd;
+        verdict[i] = (u8)verify_curve_side(SV_KIND_ECDSA33, work + i, key33 + 33 * i, sig64 + 64 * i, gtab, tab, &kd);
+        if (aux) aux[i] = (u8)((kd ? 1u : 0u) | ((work[i].flags & SV_WF_PARSED) ? 2u : 0u));
+    }
+    while (aux && todo_key) {
+        int i = 0;
+        while (!((todo_key >> i) & 1u)) i++;
+        todo_key &= todo_key - 1u;
+        ge Q;
+        bool kd = key_decode(Q, SV_KIND_ECDSA33, key33 + 33 * i);
+        aux[i] = (u8)((kd ? 1u : 0u) | ((work[i].flags & SV_WF_PARSED) ? 2u : 0u));
     }
 }
 
@@ -833,6 +846,7 @@ SV_HD void schnorr_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8
         if (i == 0) pre[0] = v; else fe_mul(pre[i], pre[i - 1], v);
     }
     fe_inv(acc, pre[cnt - 1]);
+    u32 todo_exact = 0;
     for (int i = cnt - 1; i >= 0; i--) {
         const sv_ns_park_schnorr* pk = reinterpret_cast<const sv_ns_park_schnorr*>(work + i);
         const u32 code = verdict[i];
@@ -869,11 +883,17 @@ SV_HD void schnorr_nosqrt_final_batch(u8* verdict, const sv_work* work, const u8
             bool good = !fe_is_zero(d) && fe_equal(yy, c) && !fe_is_odd(y) && !fe_is_odd(yr);
             verdict[i] = good ? 1 : 0;
         } else if (code == SV_NS_EXACT) {
-            qtab_entry tab[8];
-            verdict[i] = (u8)verify_curve_side(SV_KIND_SCHNORR, work + i, xonly32 + 32 * i, sig64 + 64 * i, gtab, tab);
+            todo_exact |= 1u << i;
         } else {
             verdict[i] = 0;
         }
+    }
+    while (todo_exact) {  // a loop of its own: see ecdsa33_nosqrt_final_batch
+        int i = 0;
+        while (!((todo_exact >> i) & 1u)) i++;
+        todo_exact &= todo_exact - 1u;
+        qtab_entry tab[8];
+        verdict[i] = (u8)verify_curve_side(SV_KIND_SCHNORR, work + i, xonly32 + 32 * i, sig64 + 64 * i, gtab, tab);
     }
 }
 
