@@ -282,6 +282,11 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        # leave two CTA slots of the persistent curve kernel free for NCCL's gather kernel: with the full grid resident it
+        # only gets an SM when a curve CTA retires and then delays a CTA of the next launch (measured at N = 2: 103.6 ->
+        # 105.4 M verifies/s, profiles/r2_n2_grid_reserve.txt; costs 0.7 % of a lone GPU, so not the N = 1 default)
+        os.environ.setdefault("SV_MAIN_GRID_RESERVE", "2")
     eng = L.SigVerifier(local)  # raises if the CUDA library or the GPU is missing: no CPU path
     eng.set_profiling(True)
     kind = L.KIND_ECDSA33
@@ -789,6 +794,8 @@ def run_c5(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    if world > 1:
+        os.environ.setdefault("SV_MAIN_GRID_RESERVE", "2")  # room for NCCL's send/recv kernels beside the persistent curve grid
     eng = L.SigVerifier(local)
     per_rank = int(os.environ.get("SV_C5_PER_RANK", 12_500_000))
     nchunk = int(os.environ.get("SV_C5_CHUNKS", 25))  # 12.5M = 2^5 x 5^8: 25 chunks of 500,000 keep every chunk a multiple of 32

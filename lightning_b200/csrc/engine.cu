@@ -1028,8 +1028,8 @@ extern "C" int sv_create(sv_ctx** out, int device) {
         CK2(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_main<SV_KIND_ECDSA33>, SV_MAIN_BLOCK, SV_MAIN_SMEM));
         if (occ < 1) occ = 1;
         ctx->main_grid = ctx->sm_count * occ;
-        // measurement aid: leave a few CTA slots of the persistent curve kernel free (e.g. for a collective's kernel that
-        // becomes ready while the grid is resident)
+        // deployment knob: leave a few CTA slots of the persistent curve kernel free for a collective's kernel that becomes
+        // ready while the grid is resident (bench.py sets 2 when it gathers verdict bitmaps over NCCL)
         if (const char* e = getenv("SV_MAIN_GRID_RESERVE")) {
             int r = atoi(e);
             if (r > 0 && r < ctx->main_grid) ctx->main_grid -= r;
