@@ -6,7 +6,14 @@
 //   K1a k_prep_inv + k_prep_finish       scalar side of ECDSA (32 signatures per thread share one s^-1 exponentiation;
 //                                        then one thread per signature: u1, u2, GLV split, recoding)
 //   K2a k_prep_schnorr                   scalar side of BIP-340 (tagged challenge hash, -e, recoding)
-//   K1b/K2b k_main<kind>                 curve side: thread per verification, persistent grid
+//   K1b/K2b k_main<kind>                 curve side: thread per verification, persistent grid.  kind 3 / 4 = compressed /
+//                                        x-only keys WITHOUT the square root (verify.cuh): the default for kinds 0 / 2
+//       k_final_ecdsa33, k_final_schnorr_ns   batched division that settles the parked linear conditions of kinds 3 / 4
+//       k_final_schnorr                  plain BIP-340 flow: affine R from the parked Jacobian R (batched inversion)
+//       k_small<kind>                    one-launch latency path for small batches (5 warps per 32 verifications)
+//       k_main_shared, k_dedup_*, k_sharedkey_build_many   one multiples table per distinct key (same-key / gossip batches)
+//       k_gossip_slice / _status, k_bip143, k_mixed_*       callers' data formats on the device (rows N1, N2, C3)
+//       k_sb_* (batch.cu)                BIP-340 batch verification by random linear combination
 //       k_pack_bitmap                    verdict bytes -> 1 bit per verification (ballot)
 //       k_pubkey_parse                   batched pubkey_from_der
 //       k_synth                          synthetic signed workload generator (benchmarks/tests)
