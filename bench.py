@@ -279,6 +279,9 @@ def run_engine(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        # the only collective is a 125 KB-per-rank gather: two channels (= two CTAs, the slots SV_MAIN_GRID_RESERVE leaves
+        # free beside the persistent curve grid) are plenty, and more could not be placed anyway
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -826,29 +829,49 @@ def run_c5(args):
             pv[o + 65 * c:o + rec] = bs[idx].reshape(-1)
             expect[g * c:(g + 1) * c] = ok
     inbuf = [torch.empty(rec, dtype=torch.uint8, device=dev) for _ in range(nchunk)]
-    stage = [torch.empty(rec, dtype=torch.uint8, device=dev) for _ in range(2)] if (rank == 0 and world > 1) else None
+    NST = 4  # staging ring on rank 0: the H2D copy of one peer's chunk runs while the previous one is on the wire
+    stage = [torch.empty(rec, dtype=torch.uint8, device=dev) for _ in range(NST)] if (rank == 0 and world > 1) else None
     verdict = torch.zeros(per_rank, dtype=torch.uint8, device=dev)
     bitmap = torch.zeros(per_rank // 32, dtype=torch.int32, device=dev)
     gathered = torch.zeros(world * bitmap.numel(), dtype=torch.int32, device=dev) if world > 1 else bitmap
     host_bits = torch.empty(world * bitmap.numel(), dtype=torch.int32, pin_memory=True) if rank == 0 else None
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    comm = torch.cuda.Stream(device=dev)
+    comm = torch.cuda.Stream(device=dev)   # NCCL send / recv / all_gather
+    h2d = torch.cuda.Stream(device=dev)    # rank 0: host -> device copies (copy engine), one step ahead of the sends
+    state = {"slot": 0, "sent": [None] * NST, "pass_done": None}
 
     def one_pass():
         evs = []
+        if state["pass_done"] is not None:
+            h2d.wait_event(state["pass_done"])  # the chunk buffers are reused: the previous pass must be through with them
         for k in range(nchunk):
-            with torch.cuda.stream(comm):
-                if rank == 0:
+            if rank == 0:
+                with torch.cuda.stream(h2d):
                     inbuf[k].copy_(pool[(0 * nchunk + k) * rec:(0 * nchunk + k + 1) * rec], non_blocking=True)
-                    for r in range(1, world):
-                        sb = stage[(k * world + r) & 1]
-                        g = r * nchunk + k
+                    ev = torch.cuda.Event()
+                    ev.record(h2d)
+                for r in range(1, world):
+                    sl = state["slot"]
+                    sb = stage[sl]
+                    g = r * nchunk + k
+                    with torch.cuda.stream(h2d):
+                        if state["sent"][sl] is not None:
+                            h2d.wait_event(state["sent"][sl])
                         sb.copy_(pool[g * rec:(g + 1) * rec], non_blocking=True)
+                        staged = torch.cuda.Event()
+                        staged.record(h2d)
+                    comm.wait_event(staged)
+                    with torch.cuda.stream(comm):
                         dist.send(sb, dst=r)
-                else:
+                        se = torch.cuda.Event()
+                        se.record(comm)
+                    state["sent"][sl] = se
+                    state["slot"] = (sl + 1) % NST
+            else:
+                with torch.cuda.stream(comm):
                     dist.recv(inbuf[k], src=0)
-                ev = torch.cuda.Event()
-                ev.record(comm)
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
             st = streams[k & 1]
             st.wait_event(ev)
             b = inbuf[k]
@@ -864,6 +887,8 @@ def run_c5(args):
                 dist.all_gather_into_tensor(gathered, bitmap)
             if rank == 0:
                 host_bits.copy_(gathered, non_blocking=True)
+            state["pass_done"] = torch.cuda.Event()
+            state["pass_done"].record(comm)
 
     def barrier():
         if world > 1:
