@@ -470,8 +470,37 @@ def run_engine(args):
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t_e.item())
-    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions
-    e2e_matches = bool(np.array_equal(np.asarray(h_out), (torch.ones(n, dtype=torch.uint8).index_fill_(0, batches[0][3].cpu(), 0)).numpy()))
+    e2e_expect = (torch.ones(n, dtype=torch.uint8).index_fill_(0, batches[0][3].cpu(), 0)).numpy()
+    e2e_matches = bool(np.array_equal(np.asarray(h_out), e2e_expect))
+    # The synchronous call above drains the GPU at every return (the thin last wave of a batch has nothing to overlap with).
+    # A host that keeps two calls in flight — two threads, each with its own context, as two CLN daemons would — gets that
+    # overlap back.  Reported beside the single-caller number, which stays the headline `e2e.value`.
+    e2e_two = None
+    if world == 1 and not quick:
+        import threading
+        eng2 = L.SigVerifier(local)
+        h_out2 = eng2.host_alloc(n)
+        half = max(3, e2e_steps // 2)
+
+        def caller(e, out, k):
+            for _ in range(k):
+                r = e.lib.sv_verify_host(e._ctx, kind, h_msg.ctypes.data, h_key.ctypes.data, h_sig.ctypes.data, n, out.ctypes.data)
+                assert r == 0
+        caller(eng2, h_out2, 2)
+        torch.cuda.synchronize()
+        th = [threading.Thread(target=caller, args=(eng, h_out, half)), threading.Thread(target=caller, args=(eng2, h_out2, half))]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt2 = time.perf_counter() - t0
+        same2 = bool(np.array_equal(np.asarray(h_out2), e2e_expect)) and bool(np.array_equal(np.asarray(h_out), e2e_expect))
+        e2e_two = {"value": 2 * half * n / dt2 if same2 else None, "unit": "verifies/s", "host_threads": 2, "contexts": 2,
+                   "steps": 2 * half, "seconds": dt2, "verdicts_as_constructed": same2}
+        e2e_matches = e2e_matches and same2
+        eng2.close()
+    clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions
 
     if rank != 0:
         if world > 1:
@@ -534,7 +563,8 @@ def run_engine(args):
         "engine": {"main_grid": info["main_grid"], "main_block": info["main_block"], "main_regs": info["main_regs"],
                    "launch_streams": 1 if streams[1] is streams[0] else 2, "l2_persist_bytes": info.get("l2_persist_bytes"), "l2_max_persist_bytes": info.get("l2_max_persist_bytes")},
         "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": n * 129, "d2h_bytes_per_step": n,
-                "steps": e2e_steps, "seconds": float(t_e.item()), "verdicts_as_constructed": e2e_matches},
+                "steps": e2e_steps, "seconds": float(t_e.item()), "verdicts_as_constructed": e2e_matches,
+                "two_callers": e2e_two},
         "sustained": sustained,
         "gpu_launches": int(launches),
         "clocks": clocks,
