@@ -31,10 +31,11 @@ def timed(fn, reps):
 def main():
     eng = L.SigVerifier(0)
     ref = util.load_ref()
-    w = util.make_signed(ref, 4096, seed=7)
-    out = {"sizes": {}, "note": "synchronous sv_verify_host calls, pageable numpy host buffers, perf_counter around the call"}
+    sizes = tuple(int(x) for x in os.environ.get("SV_LATENCY_SIZES", "1,4,32,483,4096").split(","))
+    w = util.make_signed(ref, max(4096, max(sizes)), seed=7)
+    out = {"small_max": eng.small_max(), "sizes": {}, "note": "synchronous sv_verify_host calls, pageable numpy host buffers, perf_counter around the call"}
     kinds = (("ecdsa33", 0, "pub33", "sig"), ("ecdsa_xy", 1, "pubxy", "sig"), ("schnorr", 2, "xonly", "ssig"))
-    for n in (1, 4, 32, 483, 4096):
+    for n in sizes:
         row = {}
         for name, kind, kk, ss in kinds:
             m, k, s = (np.ascontiguousarray(w[x][:n]) for x in ("msg", kk, ss))
