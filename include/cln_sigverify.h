@@ -74,7 +74,7 @@ size_t sv_key_size(int kind);
 int sv_verify_host(sv_ctx *ctx, int kind, const uint8_t *msg32, const uint8_t *key, const uint8_t *sig64,
                    size_t n, uint8_t *verdicts);
 
-/* Batches of at most `small_max` signatures (default 2048, capacity 8192; 0 disables) take the LATENCY path: one launch
+/* Batches of at most `small_max` signatures (default = capacity = 8192; 0 disables) take the LATENCY path: one launch
  * of a kernel that spreads each verification over three warps (key side / scalar side in parallel, then the two GLV
  * half-ladders and the fixed-base comb in parallel, joined by full Jacobian additions), inputs and verdicts passing
  * through a pinned, device-mapped staging block (no copy commands, no allocation).  Larger batches take the throughput
@@ -127,7 +127,7 @@ int sv_set_l2_policy(sv_ctx *ctx, int on);
 int sv_verify_schnorr_batch_host(sv_ctx *ctx, const uint8_t *msg32, const uint8_t *xonly32, const uint8_t *sig64, size_t n,
                                  const uint8_t *seed32, uint8_t *verdicts, uint32_t *groups_total, uint32_t *groups_failed);
 
-/* Key de-duplication: sv_verify_gossip_host looks for repeated keys in batches of >= 4096 signatures
+/* Key de-duplication: sv_verify_gossip_host looks for repeated keys in batches above the small-batch limit (and >= 4096 signatures)
  * (exact hash table over the 33 key bytes, on the device); when at least 40 % of the items repeat a key, every DISTINCT
  * key is decoded and its multiples table built once and the curve kernel indexes those tables.  Verdicts are unchanged.
  * sv_set_dedup(ctx, 0) switches the search off; sv_last_distinct_keys reports what the last gossip batch contained. */

@@ -824,7 +824,9 @@ __global__ void __launch_bounds__(256) k_probe_addc(int iters, u32* sink) {
 #define SV_NSLOTS 2
 #define SV_SMALL_CAP 8192           // items the pinned small-batch staging block holds
 #ifndef SV_SMALL_MAX_DEFAULT
-#define SV_SMALL_MAX_DEFAULT 2048   // largest batch sent down the small-batch path (SV_SMALL_MAX overrides; 0 disables)
+// largest batch sent down the small-batch path (SV_SMALL_MAX overrides; 0 disables).  Measured (profiles/r2_latency_paths_1k_8k.txt):
+// 4,096 signatures 480 us against 1,248 us on the throughput kernels, 8,192 signatures 661 against 1,272 us
+#define SV_SMALL_MAX_DEFAULT 8192
 #endif
 struct sv_queue_item {
     int kind;
@@ -1133,7 +1135,8 @@ extern "C" int sv_get_info(const sv_ctx* ctx, sv_info* info) {
 // the ordinary path, < 0 on error.  Synchronises the stream once (the number of distinct keys sizes the table array).
 static int launch_verify_dedup(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key, const u8* d_sig, size_t n,
                                u8* d_verdict, cudaStream_t st, u8* d_aux, u32* distinct_out) {
-    if (kind == SV_KIND_SCHNORR || n < 4096 || n > 0x7FFFFFFFu) return 0;
+    // batches the small-batch kernel takes are faster there than through the search (one launch, ~0.5 ms)
+    if (kind == SV_KIND_SCHNORR || n < 4096 || n <= ctx->small_max || n > 0x7FFFFFFFu) return 0;
     const int keylen = (int)sv_key_size(kind);
     u32 cap = 1;
     while (cap < 2 * n) cap <<= 1;

@@ -35,17 +35,17 @@ def both(engine):
 
 
 def test_small_path_random_corrupted_ragged(engine, ref, both):
-    w = util.corrupt(util.make_signed(ref, 2600, seed=77), every=5)
+    w = util.corrupt(util.make_signed(ref, 8200, seed=77), every=5)
     for kind, (k, s) in enumerate(KINDS):
         want = util.ref_verify(ref, kind, w["msg"], w[k], w[s], threads=4)
-        for n in (1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 95, 96, 97, 483, 1000, 2047, 2048, 2049, 2600):
+        for n in (1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 95, 96, 97, 483, 1000, 2047, 2048, 2049, 2600, 8191, 8192, 8193, 8200):
             a, b = both(lambda: engine.verify(kind, w["msg"][:n], w[k][:n], w[s][:n]))
             assert np.array_equal(a, want[:n]), (kind, n, "small")
             assert np.array_equal(b, want[:n]), (kind, n, "throughput")
         o = 1234  # a window that does not start at item 0
         a, b = both(lambda: engine.verify(kind, w["msg"][o:o + 40], w[k][o:o + 40], w[s][o:o + 40]))
         assert np.array_equal(a, want[o:o + 40]) and np.array_equal(b, want[o:o + 40])
-    assert engine.small_max() == 2048
+    assert engine.small_max() == 8192
 
 
 def test_small_path_mutations_adversarial_golden(engine, ref, both):

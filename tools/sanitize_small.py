@@ -34,7 +34,7 @@ eng.set_small_max(0)
 for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ssig")]):
     got = eng.verify(kind, w["msg"], w[k], w[s])
     assert np.array_equal(got, util.ref_verify(ref, kind, w["msg"], w[k], w[s])), kind
-eng.set_small_max(2048)
+eng.set_small_max(8192)
 print("throughput kernels on a small batch ok")
 kinds = (np.arange(300) % 3).astype(np.uint8)
 key = np.zeros((300, 64), np.uint8)
