@@ -485,6 +485,7 @@ def run_engine(args):
         half = max(3, e2e_steps // 2)
 
         def caller(e, out, k):
+            torch.cuda.set_device(local)  # a new host thread starts on device 0: without this, every call on rank r > 0 switches devices
             for _ in range(k):
                 r = e.lib.sv_verify_host(e._ctx, kind, h_msg.ctypes.data, h_key.ctypes.data, h_sig.ctypes.data, n, out.ctypes.data)
                 assert r == 0

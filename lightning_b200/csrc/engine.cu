@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(SV_MAIN_BLOCK, SV_MAIN_MINB)
 // ---- small-batch path (verify.cuh "small-batch path"): one CTA = 5 warps x up to 32 items.  The inputs may live in host-mapped pinned memory (zero-copy: the CTA pulls its items into shared memory
 // with warp-coalesced loads) or in device memory.  aux (optional): bit 0 = key decoded, bit 1 = signature encoding parsed.
 #define SV_SMALL_ITEMS 32
-template <int KIND>
+template <int KIND, bool NOSQRT>
 __global__ void __launch_bounds__(160, 1)
     k_small(const u8* __restrict__ msg, const u8* __restrict__ key, const u8* __restrict__ sig, size_t n,
             const ge_mem* __restrict__ gtab, u8* __restrict__ verdict, u8* __restrict__ aux) {
@@ -264,8 +264,9 @@ __global__ void __launch_bounds__(160, 1)
     const u8* m = in_msg + 32 * j;
     const u8* k = in_key + keylen * j;
     const u8* sg = in_sig + 64 * j;
-    if (warp == 0) small_key_side(KIND, k, it);
-    else if (warp == 1) small_scalar_side(KIND, m, k, sg, it);
+    if (warp == 0) {
+        if (NOSQRT) small_key_side_ns(KIND, k, it); else small_key_side(KIND, k, it);
+    } else if (warp == 1) small_scalar_side(KIND, m, k, sg, it);
     __syncthreads();
     // phase B: warps 0..3 run the half ladders on lane PAIRS (warp w: half w >> 1, items 16 (w & 1) + lane / 2), warp 4 the comb
     if (warp < 4) {
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(160, 1)
     }
     __syncthreads();
     if (warp == 0) {
-        bool kd;
-        u32 v = small_finish(KIND, it, sg, &kd);
+        bool kd = false;
+        u32 v = NOSQRT ? small_finish_ns(KIND, it, k, sg, gtab, aux ? &kd : nullptr) : small_finish(KIND, it, sg, &kd);
         if (active) {
             verdict[base + lane] = (u8)v;
             if (aux) aux[base + lane] = (u8)((kd ? 1u : 0u) | ((it->w.flags & SV_WF_PARSED) ? 2u : 0u));
@@ -1226,9 +1227,12 @@ static int launch_small(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key,
     unsigned grid = (unsigned)((n + SV_SMALL_ITEMS - 1) / SV_SMALL_ITEMS);
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
-    if (kind == SV_KIND_ECDSA33) k_small<SV_KIND_ECDSA33><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
-    else if (kind == SV_KIND_ECDSA_XY) k_small<SV_KIND_ECDSA_XY><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
-    else k_small<SV_KIND_SCHNORR><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    // compressed and x-only keys: without the square root unless switched off (verify.cuh)
+    if (kind == SV_KIND_ECDSA33 && ctx->nosqrt) k_small<SV_KIND_ECDSA33, true><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else if (kind == SV_KIND_ECDSA33) k_small<SV_KIND_ECDSA33, false><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else if (kind == SV_KIND_ECDSA_XY) k_small<SV_KIND_ECDSA_XY, false><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else if (ctx->nosqrt) k_small<SV_KIND_SCHNORR, true><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    else k_small<SV_KIND_SCHNORR, false><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], st);
     ctx->launches += 1;
     CK(cudaGetLastError());

@@ -563,6 +563,65 @@ struct alignas(16) sv_ns_park {
     u32 d[8], b[8], c[8], pad[8];
 };
 
+// The linear form itself.  S = (X1, Y1, y*Zs) with y^2 = c, T = (X2, Y2, Z2), both finite.  Jacobian addition S + T with the
+// powers of y collected:  X3 = A - y*B,  Z3 = y*z3,  so  x(S + T) == r  <=>  y*B == D := A - r*c*z3^2.
+// Returns true when the form does not apply (equal x coordinates, or B == 0): the caller falls back to the plain path.
+// With ext != nullptr also  Y3 = E + y*F  is worked out and  ext[0] = N = E*B + F*D,  ext[1] = CG = c*z3^3  (BIP-340:
+// y(S + T) = N / (D*CG) once y = D/B).
+SV_HD bool ns_linear_form(fe& D, fe& B, const fe& X1, const fe& Y1, const fe& Zs, const gej& T, const fe& c, const fe& rfe,
+                          fe* ext = nullptr) {
+    fe z2z2, t, U1, S1, czs2, s2p, H, z3, A, HH, V, K, W0;
+    fe_sqr(z2z2, T.z);
+    fe_mul(U1, X1, z2z2);            // U1 = X1 Z2^2
+    fe_mul(t, T.z, z2z2);
+    fe_mul(S1, Y1, t);               // S1 = Y1 Z2^3
+    fe_sqr(t, Zs);
+    fe_mul(czs2, c, t);              // (y Zs)^2
+    fe_mul(H, T.x, czs2);            // U2 = X2 (y Zs)^2
+    fe_sub(H, H, U1);                // H = U2 - U1
+    fe_mul(t, Zs, czs2);
+    fe_mul(s2p, T.y, t);             // S2 = y * s2p,  s2p = Y2 c Zs^3
+    bool exact = fe_is_zero(H);      // equal x coordinates: doubling or infinity, depending on the sign of y
+    fe_mul(z3, H, Zs);
+    fe_mul(z3, z3, T.z);             // Z3 = y * z3
+    fe_mul(B, s2p, S1);
+    fe_dbl(B, B);                    // (S2 - S1)^2 = c s2p^2 + S1^2 - y * B
+    exact = exact || fe_is_zero(B);
+    fe_sqr(t, s2p);
+    fe_mul(A, c, t);
+    fe_sqr(t, S1);
+    fe_add(A, A, t);
+    fe_sqr(HH, H);
+    fe_mul(K, H, HH);                // H^3
+    fe_sub(A, A, K);
+    fe_mul(V, U1, HH);
+    fe_sub(A, A, V);
+    fe_sub(A, A, V);                 // - 2 U1 H^2 :  X3 = A - y B
+    fe_sqr(t, z3);
+    fe_mul(W0, c, t);                // Z3^2 = c z3^2
+    fe_mul(t, rfe, W0);
+    fe_sub(D, A, t);                 // X3 == r Z3^2  <=>  y B == D
+    if (ext) {
+        // Y3 = (y s2p - S1)(V - X3) - S1 H^3 = E + y F
+        fe E, F;
+        fe_mul(K, K, S1);            // K = S1 H^3
+        fe_sub(V, V, A);             // V - A
+        fe_mul(E, c, s2p);
+        fe_mul(E, E, B);
+        fe_mul(t, S1, V);
+        fe_sub(E, E, t);
+        fe_sub(E, E, K);             // E = c s2p B - S1 (V - A) - K
+        fe_mul(F, s2p, V);
+        fe_mul(t, S1, B);
+        fe_sub(F, F, t);             // F = s2p (V - A) - S1 B
+        fe_mul(E, E, B);
+        fe_mul(F, F, D);
+        fe_add(ext[0], E, F);        // N = E B + F D
+        fe_mul(ext[1], W0, z3);      // CG = c z3^3
+    }
+    return exact;
+}
+
 // Curve side for one item.  Returns 0 (verdict 0 is final), SV_NS_PENDING (park filled) or SV_NS_EXACT.  `park` may alias w.
 SV_HD u32 ecdsa33_nosqrt_curve_side(const sv_work* w, const u8* key33, const u8* sig64, const ge_mem* gtab, qtab_entry* tab,
                                     sv_ns_park* park, bool store, unsigned sync_threads = 0) {
@@ -602,42 +661,12 @@ SV_HD u32 ecdsa33_nosqrt_curve_side(const sv_work* w, const u8* key33, const u8*
     fe_sqr(c, x);
     fe_mul(c, c, x);
     fe_add(c, c, seven);
-    fe X1, Y1, Zs, z2z2, t, U1, S1, czs2, s2p, H, z3, A, B, HH, D;
+    fe X1, Y1, Zs, B, D, rfe;
     fe_from_words(X1, tab[0].x);
     fe_from_words(Y1, tab[0].y);
     fe_from_words(Zs, tab[0].h);
-    fe_sqr(z2z2, T.z);
-    fe_mul(U1, X1, z2z2);            // U1 = X1 Z2^2
-    fe_mul(t, T.z, z2z2);
-    fe_mul(S1, Y1, t);               // S1 = Y1 Z2^3
-    fe_sqr(t, Zs);
-    fe_mul(czs2, c, t);              // (y Zs)^2
-    fe_mul(H, T.x, czs2);            // U2 = X2 (y Zs)^2
-    fe_sub(H, H, U1);                // H = U2 - U1
-    fe_mul(t, Zs, czs2);
-    fe_mul(s2p, T.y, t);             // S2 = y * s2p,  s2p = Y2 c Zs^3
-    exact = exact || fe_is_zero(H);  // equal x coordinates: doubling or infinity, depending on y
-    fe_mul(z3, H, Zs);
-    fe_mul(z3, z3, T.z);             // Z3 = y * z3
-    fe_mul(B, s2p, S1);
-    fe_dbl(B, B);                    // (S2 - S1)^2 = c s2p^2 + S1^2 - y * B
-    exact = exact || fe_is_zero(B);
-    fe_sqr(t, s2p);
-    fe_mul(A, c, t);
-    fe_sqr(t, S1);
-    fe_add(A, A, t);
-    fe_sqr(HH, H);
-    fe_mul(t, H, HH);
-    fe_sub(A, A, t);                 // - H^3
-    fe_mul(t, U1, HH);
-    fe_sub(A, A, t);
-    fe_sub(A, A, t);                 // - 2 U1 H^2 :  X3 = A - y B
-    fe_sqr(t, z3);
-    fe_mul(t, c, t);                 // Z3^2
-    fe rfe;
     fe_set_b32(rfe, sig64);          // r < n < p
-    fe_mul(t, rfe, t);
-    fe_sub(D, A, t);                 // X3 == r Z3^2  <=>  y B == D
+    exact = ns_linear_form(D, B, X1, Y1, Zs, T, c, rfe) || exact;
     if (!ok) return 0u;
     if (exact) return SV_NS_EXACT;
     if (store) {
@@ -764,64 +793,19 @@ SV_HD u32 schnorr_nosqrt_curve_side(const sv_work* w, const u8* xonly32, const u
     fe_sqr(c, x);
     fe_mul(c, c, x);
     fe_add(c, c, seven);
-    fe X1, Y1, Zs, z2z2, t, U1, S1, czs2, s2p, H, z3, A, B, HH, D, V, K, E, F, W0;
+    fe X1, Y1, Zs, B, D, rfe, ext[2];
     fe_from_words(X1, tab[0].x);
     fe_from_words(Y1, tab[0].y);
     fe_from_words(Zs, tab[0].h);
-    fe_sqr(z2z2, T.z);
-    fe_mul(U1, X1, z2z2);
-    fe_mul(t, T.z, z2z2);
-    fe_mul(S1, Y1, t);
-    fe_sqr(t, Zs);
-    fe_mul(czs2, c, t);
-    fe_mul(H, T.x, czs2);
-    fe_sub(H, H, U1);
-    fe_mul(t, Zs, czs2);
-    fe_mul(s2p, T.y, t);
-    exact = exact || fe_is_zero(H);
-    fe_mul(z3, H, Zs);
-    fe_mul(z3, z3, T.z);
-    fe_mul(F, s2p, S1);              // s2p S1 (kept: F needs S1 * B = 2 S1 * this)
-    fe_dbl(B, F);
-    exact = exact || fe_is_zero(B);
-    fe_sqr(t, s2p);
-    fe_mul(A, c, t);
-    fe_sqr(t, S1);
-    fe_add(A, A, t);
-    fe_sqr(HH, H);
-    fe_mul(K, H, HH);                // H^3
-    fe_sub(A, A, K);
-    fe_mul(V, U1, HH);
-    fe_sub(A, A, V);
-    fe_sub(A, A, V);                 // X3 = A - y B
-    fe_mul(K, K, S1);                // K = S1 H^3
-    fe_sub(V, V, A);                 // V - A
-    // Y3 = (y s2p - S1)(V - X3) - K = E + y F
-    fe_mul(E, c, s2p);
-    fe_mul(E, E, B);
-    fe_mul(t, S1, V);
-    fe_sub(E, E, t);
-    fe_sub(E, E, K);                 // E = c s2p B - S1 (V - A) - K
-    fe_mul(F, s2p, V);
-    fe_mul(t, S1, B);
-    fe_sub(F, F, t);                 // F = s2p (V - A) - S1 B
-    fe_sqr(t, z3);
-    fe_mul(W0, c, t);                // Z3^2 = c z3^2
-    fe rfe;
     fe_set_b32(rfe, sig64);          // r < p checked by the scalar side (flags)
-    fe_mul(t, rfe, W0);
-    fe_sub(D, A, t);                 // y B == D
-    fe_mul(E, E, B);
-    fe_mul(F, F, D);
-    fe_add(E, E, F);                 // N = E B + F D
-    fe_mul(W0, W0, z3);              // CG = c z3^3
+    exact = ns_linear_form(D, B, X1, Y1, Zs, T, c, rfe, ext) || exact;
     if (!ok) return 0u;
     if (exact) return SV_NS_EXACT;
     if (store) {
         fe_to_words(park->d, D);
         fe_to_words(park->b, B);
-        fe_to_words(park->n, E);
-        fe_to_words(park->cg, W0);
+        fe_to_words(park->n, ext[0]);
+        fe_to_words(park->cg, ext[1]);
     }
     return SV_NS_PENDING;
 }
@@ -1043,6 +1027,98 @@ SV_HD u32 small_finish(int kind, sv_small_item* it, const u8* sig64, bool* key_o
     u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64, true) : ecdsa_final(R, sig64, flags);
     return ok ? v : 0u;
 }
+// ---- small-batch path without the square root (kinds ECDSA33 and SCHNORR; see "without the square root" above) ----------
+// phase A builds the table of Q' = (c x, c^2) on the isomorphic curve, the half ladders and the comb run unchanged, and the
+// finish assembles the linear form from S' = R1 + R2 and T and settles it with one field inversion per signature (no batch
+// to share it with here).  key_ok then only says "the key's encoding is acceptable"; whether x is on the curve comes out of
+// the final comparison.  Configurations the linear form does not cover are verified by the plain sequential path.
+SV_HD void small_key_side_ns(int kind, const u8* key, sv_small_item* it) {
+    fe x, c, seven;
+    bool ok;
+    if (kind == SV_KIND_ECDSA33) {
+        const u8 pfx = key[0];
+        ok = (pfx == 2 || pfx == 3);            // eckey_impl.h:17
+        ok = fe_set_b32(x, key + 1) && ok;
+    } else {
+        ok = fe_set_b32(x, key);                // extrakeys/main_impl.h:32
+    }
+    it->key_ok = ok ? 1u : 0u;
+    fe_set_u32(seven, 7);
+    fe_sqr(c, x);
+    fe_mul(c, c, x);
+    fe_add(c, c, seven);
+    ge Qp;
+    fe_mul(Qp.x, c, x);
+    fe_sqr(Qp.y, c);
+    fe zc;
+    qtable_build(it->tab, zc, Qp);
+    fe_to_words(it->zc, zc);
+}
+
+// key_ok (optional): whether the key decodes (secp256k1_ec_pubkey_parse / xonly_pubkey_parse would accept it)
+SV_HD u32 small_finish_ns(int kind, sv_small_item* it, const u8* key, const u8* sig64, const ge_mem* gtab, bool* key_ok = nullptr) {
+    const u32 flags = it->w.flags;
+    const bool ok = (flags & SV_WF_VALID) != 0 && it->key_ok != 0;
+    gej S, T;
+    small_jac_load(S, &it->r1);
+    small_jac_load(T, &it->r2);
+    gej_add_gej(S, S, T);   // on the isomorphic, scaled curve: the formulas never use the curve constant
+    fe zc;
+    fe_from_words(zc, it->zc);
+    fe_mul(S.z, S.z, zc);
+    small_jac_load(T, &it->p3);
+    bool exact = S.inf || T.inf || (kind == SV_KIND_ECDSA33 && (flags & SV_WF_R_PLUS_N) != 0);
+    fe x, c, seven, rfe, D, B, ext[2];
+    fe_set_b32(x, kind == SV_KIND_ECDSA33 ? key + 1 : key);
+    fe_set_u32(seven, 7);
+    fe_sqr(c, x);
+    fe_mul(c, c, x);
+    fe_add(c, c, seven);
+    fe_set_b32(rfe, sig64);
+    exact = ns_linear_form(D, B, S.x, S.y, S.z, T, c, rfe, kind == SV_KIND_SCHNORR ? ext : nullptr) || exact;
+    u32 v = 0;
+    bool kd = false, kd_known = false;
+    if (ok && exact) {
+        // rare (a signer steering the scalars): the plain path, one thread
+        v = verify_curve_side(kind, &it->w, key, sig64, gtab, it->tab, &kd);
+        kd_known = true;
+    } else if (ok) {
+        fe inv, y, yy, t;
+        if (kind == SV_KIND_SCHNORR) {
+            fe w;
+            fe_mul(w, D, ext[1]);          // W = D CG
+            fe_mul(t, w, B);
+            bool zero = fe_is_zero(t);     // D == 0: y would be 0, never a root of c != 0
+            if (zero) fe_set_u32(t, 1);
+            fe_inv_var(inv, t);            // 1 / (B W)
+            fe_mul(t, w, inv);             // 1 / B
+            fe_mul(y, D, t);
+            fe_normalize(y);
+            fe_sqr(yy, y);
+            fe yr;
+            fe_mul(t, B, inv);             // 1 / W
+            fe_mul(yr, ext[0], t);         // y(R) = N / W
+            fe_normalize(yr);
+            v = (!zero && fe_equal(yy, c) && !fe_is_odd(y) && !fe_is_odd(yr)) ? 1u : 0u;   // main_impl.h:255-264
+        } else {
+            fe_inv_var(inv, B);
+            fe_mul(y, D, inv);
+            fe_normalize(y);
+            fe_sqr(yy, y);
+            v = (fe_equal(yy, c) && (fe_is_odd(y) == (key[0] == 3))) ? 1u : 0u;
+        }
+        if (v) { kd = true; kd_known = true; }
+    }
+    if (key_ok) {
+        if (!kd_known) {
+            ge Q;
+            kd = key_decode(Q, kind, key);
+        }
+        *key_ok = kd;
+    }
+    return v;
+}
+
 // ---- half ladder on a PAIR of lanes -------------------------------------------------------------------------------
 // A half ladder is one dependent chain of 128 doublings and 33 additions: 1,259 field multiplications one after another
 // set the latency of a lone verification.  Inside one doubling / addition, however, several multiplications are independent
@@ -1195,13 +1271,14 @@ SV_HD void small_half_ladder_pair(const pair_lane& L, sv_small_item* it, int hal
 
 // the three phases run one after another (host build of the kernel source, tests/host_emul)
 SV_HD u32 verify_small_sequential(int kind, const u8* msg32, const u8* key, const u8* sig64, const ge_mem* gtab,
-                                  sv_small_item* it) {
-    small_key_side(kind, key, it);
+                                  sv_small_item* it, bool nosqrt = false) {
+    nosqrt = nosqrt && kind != SV_KIND_ECDSA_XY;
+    if (nosqrt) small_key_side_ns(kind, key, it); else small_key_side(kind, key, it);
     small_scalar_side(kind, msg32, key, sig64, it);
     small_half_ladder(it, 0);
     small_half_ladder(it, 1);
     small_comb(it, gtab);
-    return small_finish(kind, it, sig64);
+    return nosqrt ? small_finish_ns(kind, it, key, sig64, gtab) : small_finish(kind, it, sig64);
 }
 
 // =================================================================================================

@@ -212,7 +212,7 @@ void emul_verify_small_batch(int kind, const u8* msg, const u8* key, const u8* s
     size_t keylen = kind == SV_KIND_ECDSA33 ? 33 : (kind == SV_KIND_ECDSA_XY ? 64 : 32);
     sv_small_item it;
     for (size_t i = 0; i < n; i++)
-        out[i] = (u8)verify_small_sequential(kind, msg + 32 * i, key + keylen * i, sig + 64 * i, g_table.data(), &it);
+        out[i] = (u8)verify_small_sequential(kind, msg + 32 * i, key + keylen * i, sig + 64 * i, g_table.data(), &it, !g_ecdsa33_exact);
 }
 
 // BIP-340 batch verification (batch.cuh), every stage on the host with the straightforward window sum: ok[i] = encoding
@@ -243,7 +243,8 @@ void emul_verify_small_pair_batch(int kind, const u8* msg, const u8* key, const 
     size_t keylen = kind == SV_KIND_ECDSA33 ? 33 : (kind == SV_KIND_ECDSA_XY ? 64 : 32);
     sv_small_item it;
     for (size_t i = 0; i < n; i++) {
-        small_key_side(kind, key + keylen * i, &it);
+        const bool ns = !g_ecdsa33_exact && kind != SV_KIND_ECDSA_XY;  // as k_small<kind, true>
+        if (ns) small_key_side_ns(kind, key + keylen * i, &it); else small_key_side(kind, key + keylen * i, &it);
         small_scalar_side(kind, msg + 32 * i, key + keylen * i, sig + 64 * i, &it);
         for (int half = 0; half < 2; half++) {
             pair_mailbox mb;
@@ -255,8 +256,16 @@ void emul_verify_small_pair_batch(int kind, const u8* msg, const u8* key, const 
             other.join();
         }
         small_comb(&it, g_table.data());
-        out[i] = (u8)small_finish(kind, &it, sig + 64 * i);
+        bool kd = false;
+        out[i] = ns ? (u8)small_finish_ns(kind, &it, key + keylen * i, sig + 64 * i, g_table.data(), g_aux ? &kd : nullptr)
+                    : (u8)small_finish(kind, &it, sig + 64 * i, &kd);
+        if (g_aux) g_aux[i] = (u8)((kd ? 1u : 0u) | ((it.w.flags & SV_WF_PARSED) ? 2u : 0u));  // as k_small
     }
+}
+void emul_verify_small_pair_batch_aux(int kind, const u8* msg, const u8* key, const u8* sig, size_t n, u8* out, u8* aux) {
+    g_aux = aux;
+    emul_verify_small_pair_batch(kind, msg, key, sig, n, out);
+    g_aux = nullptr;
 }
 
 // full verification of a batch, same data flow as the kernels (prep in groups of SV_PREP_BATCH)

@@ -469,5 +469,20 @@ def test_ecdsa33_without_square_root_vs_plain_path(emul, ref):
                 assert emul.emul_last_exact_count() == 10
             for v in json.load(open(os.path.join(GOLD, "bip340.json"))):
                 assert emul_verify(emul, 2, h(v["msg32"], 32), h(v["xonly"], 32), h(v["sig64"], 64))[0] == v["expected"], (exact, v["index"])
+            # the small-batch schedule follows the same switch (k_small<kind, nosqrt>): single-lane and lane-pair half ladders,
+            # verdicts and the per-item byte
+            sm = np.zeros(n_items, np.uint8)
+            emul.emul_verify_small_batch(0, P(w["msg"]), P(w["pub33"]), P(w["sig"]), ctypes.c_size_t(n_items), P(sm))
+            assert np.array_equal(sm, want), exact
+            m = 120
+            out2, aux2 = np.zeros(m, np.uint8), np.zeros(m, np.uint8)
+            emul.emul_verify_small_pair_batch_aux(0, P(w["msg"]), P(w["pub33"]), P(w["sig"]), ctypes.c_size_t(m), P(out2), P(aux2))
+            assert np.array_equal(out2, want[:m]) and np.array_equal(aux2, aux[:m]), exact
+            sm = np.zeros(ws["msg"].shape[0], np.uint8)
+            emul.emul_verify_small_batch(2, P(ws["msg"]), P(ws["xonly"]), P(ws["ssig"]), ctypes.c_size_t(sm.shape[0]), P(sm))
+            assert np.array_equal(sm, swant), exact
+            sm = np.zeros(amsg.shape[0], np.uint8)
+            emul.emul_verify_small_batch(0, P(amsg), P(apub33), P(asig), ctypes.c_size_t(sm.shape[0]), P(sm))
+            assert np.array_equal(sm, awant), exact
     finally:
         emul.emul_set_ecdsa33_exact(0)
