@@ -1227,9 +1227,11 @@ static int launch_small(sv_ctx* ctx, int kind, const u8* d_msg, const u8* d_key,
     unsigned grid = (unsigned)((n + SV_SMALL_ITEMS - 1) / SV_SMALL_ITEMS);
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], st);
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], st);
-    // compressed and x-only keys: without the square root unless switched off (verify.cuh)
-    if (kind == SV_KIND_ECDSA33 && ctx->nosqrt) k_small<SV_KIND_ECDSA33, true><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
-    else if (kind == SV_KIND_ECDSA33) k_small<SV_KIND_ECDSA33, false><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
+    // x-only keys: without the square root unless switched off (verify.cuh).  BIP-340 needs a field inversion at the end
+    // either way, so dropping the square root is pure gain (n = 1: 471 -> 423 us).  For compressed-key ECDSA the division
+    // D/B would be an inversion the plain flow does not have, as long as the square root it replaces and divergent across
+    // lanes: measured slower (n = 32: 430 -> 529 us, profiles/r2_latency_small_nosqrt.json), so kind 0 stays on the plain flow.
+    if (kind == SV_KIND_ECDSA33) k_small<SV_KIND_ECDSA33, false><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
     else if (kind == SV_KIND_ECDSA_XY) k_small<SV_KIND_ECDSA_XY, false><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
     else if (ctx->nosqrt) k_small<SV_KIND_SCHNORR, true><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);
     else k_small<SV_KIND_SCHNORR, false><<<grid, 160, 0, st>>>(d_msg, d_key, d_sig, n, ctx->d_gtab, d_verdict, d_aux);

@@ -1027,7 +1027,10 @@ SV_HD u32 small_finish(int kind, sv_small_item* it, const u8* sig64, bool* key_o
     u32 v = (kind == SV_KIND_SCHNORR) ? schnorr_final(R, sig64, true) : ecdsa_final(R, sig64, flags);
     return ok ? v : 0u;
 }
-// ---- small-batch path without the square root (kinds ECDSA33 and SCHNORR; see "without the square root" above) ----------
+// ---- small-batch path without the square root (see "without the square root" above) ---------------------------------
+// Written for both key kinds; the engine uses it for BIP-340 only (k_small<SCHNORR, true>) — for compressed-key ECDSA the one
+// division per signature costs what the square root cost (measured, engine.cu launch_small), so kind 0 keeps the plain flow
+// in the small-batch kernel.  The host build tests both.
 // phase A builds the table of Q' = (c x, c^2) on the isomorphic curve, the half ladders and the comb run unchanged, and the
 // finish assembles the linear form from S' = R1 + R2 and T and settles it with one field inversion per signature (no batch
 // to share it with here).  key_ok then only says "the key's encoding is acceptable"; whether x is on the curve comes out of
