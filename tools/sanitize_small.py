@@ -45,7 +45,9 @@ for kind, (k, s) in enumerate([("pub33", "sig"), ("pubxy", "sig"), ("xonly", "ss
     sig[sel] = w[s][sel]
 print("mixed", eng.verify_mixed(kinds, w["msg"], key, sig).sum())
 big = [m for m in msgs if m[:2] in (b"\x01\x00", b"\x01\x01")][:1500]
+eng.set_small_max(0)  # the key search only runs above the small-batch limit
 st = eng.verify_gossip(big)
+eng.set_small_max(8192)
 print("gossip with de-duplication", int((st == 0).sum()), "of", len(big), "distinct keys", eng.last_distinct_keys())
 w2 = util.make_signed(ref, 1100, seed=4)
 v, gt, gf = eng.verify_schnorr_batch(w2["msg"], w2["xonly"], w2["ssig"], seed32=bytes(32))
