@@ -347,6 +347,44 @@ void emul_verify_batch_aux(int kind, const u8* msg, const u8* key, const u8* sig
     emul_verify_batch(kind, msg, key, sig, n, out);
     g_aux = nullptr;
 }
+// Algebra of the linear form (verify.cuh ns_linear_form) against the plain Jacobian addition.  P1, P2: affine curve points
+// (x || y, 8 limbs each), zr, tz, y: non-zero field elements.  S = P1 in Jacobian coordinates with Z = zr, written as
+// (X, Y, y * Zs) with Zs = zr / y; T = P2 with Z = tz; c = y^2; r = x(S + T).  Checked: D == y*B, N == Y3*B, CG*y == Z3^3,
+// and that r + 1 breaks D == y*B.  Returns a bit per check (15 = all hold), or -1 if the form reports an exceptional input.
+int emul_ns_linear_check(const u32* p1, const u32* p2, const u32* zr_, const u32* tz_, const u32* y_) {
+    fe x1, y1, x2, y2, zr, tz, y, t, zz;
+    for (int i = 0; i < 8; i++) { x1.v[i] = p1[i]; y1.v[i] = p1[8 + i]; x2.v[i] = p2[i]; y2.v[i] = p2[8 + i]; zr.v[i] = zr_[i]; tz.v[i] = tz_[i]; y.v[i] = y_[i]; }
+    gej S, T, R;
+    fe_sqr(zz, zr); fe_mul(S.x, x1, zz); fe_mul(t, zz, zr); fe_mul(S.y, y1, t); S.z = zr; S.inf = 0;
+    fe_sqr(zz, tz); fe_mul(T.x, x2, zz); fe_mul(t, zz, tz); fe_mul(T.y, y2, t); T.z = tz; T.inf = 0;
+    gej_add_gej(R, S, T);
+    if (R.inf) return -1;
+    fe c, yi, Zs, zi, rfe, D, B, ext[2];
+    fe_sqr(c, y);
+    fe_inv(yi, y);
+    fe_mul(Zs, zr, yi);
+    fe_inv(zi, R.z);
+    fe_sqr(t, zi);
+    fe_mul(rfe, R.x, t);  // affine x of S + T
+    fe_normalize(rfe);
+    if (ns_linear_form(D, B, S.x, S.y, Zs, T, c, rfe, ext)) return -1;
+    int ok = 0;
+    fe_mul(t, y, B);
+    if (fe_equal(t, D)) ok |= 1;
+    fe_mul(t, R.y, B);
+    if (fe_equal(t, ext[0])) ok |= 2;
+    fe z3c;
+    fe_sqr(z3c, R.z); fe_mul(z3c, z3c, R.z);
+    fe_mul(t, ext[1], y);
+    if (fe_equal(t, z3c)) ok |= 4;
+    fe one, r2, D2, B2;
+    fe_set_u32(one, 1);
+    fe_add(r2, rfe, one);
+    ns_linear_form(D2, B2, S.x, S.y, Zs, T, c, r2);
+    fe_mul(t, y, B2);
+    if (!fe_equal(t, D2) && fe_equal(B2, B)) ok |= 8;
+    return ok;
+}
 // kinds ECDSA33 and SCHNORR: 1 = the plain flow with the square root, 0 = the flow without it (the engine's default)
 void emul_set_ecdsa33_exact(int on) { g_ecdsa33_exact = on; }
 size_t emul_last_exact_count(void) { return g_last_exact; }

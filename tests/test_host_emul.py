@@ -486,3 +486,24 @@ def test_ecdsa33_without_square_root_vs_plain_path(emul, ref):
             assert np.array_equal(sm, awant), exact
     finally:
         emul.emul_set_ecdsa33_exact(0)
+
+
+def test_linear_form_algebra_against_plain_jacobian_addition(emul, ref):
+    """The identity the no-sqrt flows rest on, checked directly on the host build: for S = (X, Y, y*Zs), T Jacobian and
+    c = y^2, ns_linear_form's D, B, N, CG satisfy D == y*B exactly when r = x(S + T), N == Y3*B and CG*y == Z3^3, with
+    S + T computed by the plain addition formulas.  200 random configurations (points from the reference's k*G)."""
+    rng = random.Random(2718)
+
+    def point():
+        k = rng.randrange(1, n)
+        out = np.zeros(64, np.uint8)
+        assert ref.ref_scalar_base_mult(P(np.frombuffer(k.to_bytes(32, "big"), np.uint8).copy()), P(out))
+        return limbs(int.from_bytes(bytes(out[:32]), "big")) + limbs(int.from_bytes(bytes(out[32:]), "big"))
+
+    def limbs(v):
+        return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    arr = lambda xs: (ctypes.c_uint32 * len(xs))(*xs)
+    emul.emul_ns_linear_check.restype = ctypes.c_int
+    for _ in range(200):
+        vals = [limbs(rng.randrange(1, p)) for _ in range(3)]
+        assert emul.emul_ns_linear_check(arr(point()), arr(point()), arr(vals[0]), arr(vals[1]), arr(vals[2])) == 15
