@@ -507,3 +507,18 @@ def test_linear_form_algebra_against_plain_jacobian_addition(emul, ref):
     for _ in range(200):
         vals = [limbs(rng.randrange(1, p)) for _ in range(3)]
         assert emul.emul_ns_linear_check(arr(point()), arr(point()), arr(vals[0]), arr(vals[1]), arr(vals[2])) == 15
+
+
+def test_no_sqrt_flows_larger_random_sample(emul, ref):
+    """10,000 reference-signed triples per kind (every third one corrupted) through the flows without the square root —
+    throughput schedule (park + batched division) and, for BIP-340, the small-batch schedule — against the reference."""
+    w = util.corrupt(util.make_signed(ref, 10000, seed=4242), every=3)
+    for kind, k, s in ((0, "pub33", "sig"), (2, "xonly", "ssig")):
+        want = util.ref_verify(ref, kind, w["msg"], w[k], w[s], threads=4)
+        got = emul_verify(emul, kind, w["msg"], w[k], w[s])
+        assert np.array_equal(got, want), kind
+        assert 6000 < want.sum() < 7000
+    sm = np.zeros(3000, np.uint8)
+    emul.emul_verify_small_batch(2, P(np.ascontiguousarray(w["msg"][:3000])), P(np.ascontiguousarray(w["xonly"][:3000])),
+                                 P(np.ascontiguousarray(w["ssig"][:3000])), ctypes.c_size_t(3000), P(sm))
+    assert np.array_equal(sm, util.ref_verify(ref, 2, w["msg"][:3000], w["xonly"][:3000], w["ssig"][:3000], threads=4))
